@@ -1,0 +1,548 @@
+// Host layer of the C ABI (pdsb_host_*): the orchestration the reference does in Rust inside each
+// `#[polars_expr] fn pl_lr*` (/root/reference/src/num_ext/linear_regression.rs:419-1283) — kwargs dispatch, null
+// policy, packing — rewritten around a device-resident, column-major design matrix:
+//   Arrow chunks --H2D (straight DMA when dtype matches and no nulls, else raw upload + K1 cast/validity)-->
+//   Z = [targets | features] in HBM  -->  K2 moments  -->  K3 solve  -->  K4 predict / K6 online / K9 report
+//   --> D2H into pooled pinned buffers handed to the caller.
+// Dropped rows (null policy skip / fill-with-null-target) are zeroed + masked instead of filtered, so no compaction
+// pass exists; the physical ones column of the reference (:180-182) is never built.
+#include "../common.h"
+#include "../kernels/kernels.h"
+#include "host.h"
+#include <cstring>
+#include <cmath>
+#include <cfloat>
+#include <strings.h>
+#include <algorithm>
+
+namespace pdsb {
+
+int parse_null_policy(const char* s, NullPolicy* out) {
+  if (!s) s = "";
+  if (!strcasecmp(s, "raise")) { *out = {NullKind::RAISE, 0.0}; return 0; }
+  if (!strcasecmp(s, "skip")) { *out = {NullKind::SKIP, 0.0}; return 0; }
+  if (!strcasecmp(s, "zero")) { *out = {NullKind::FILL, 0.0}; return 0; }
+  if (!strcasecmp(s, "one")) { *out = {NullKind::FILL, 1.0}; return 0; }
+  if (!strcasecmp(s, "ignore")) { *out = {NullKind::IGNORE, 0.0}; return 0; }
+  if (!strcasecmp(s, "skip_window")) { *out = {NullKind::SKIP_WINDOW, 0.0}; return 0; }
+  char* end = nullptr;
+  double v = strtod(s, &end);
+  if (end != s && end && *end == '\0') { *out = {NullKind::FILL, v}; return 0; }
+  set_error("Invalid NullPolicy.");
+  return 1;
+}
+
+int solver_from_string(const char* s) {
+  if (s && !strcmp(s, "svd")) return PDSB_SOLVER_SVD;
+  if (s && !strcmp(s, "choleskey")) return PDSB_SOLVER_CHOLESKEY;
+  return PDSB_SOLVER_QR;
+}
+
+int se_type_from_string(const char* s) {
+  if (!s) return 0;
+  if (!strcmp(s, "hc0")) return 1;
+  if (!strcmp(s, "hc1")) return 2;
+  if (!strcmp(s, "hc2")) return 3;
+  if (!strcmp(s, "hc3")) return 4;
+  return 0;
+}
+
+namespace {
+
+template <typename T> struct DT;
+template <> struct DT<float> { static constexpr int code = PDSB_F32; };
+template <> struct DT<double> { static constexpr int code = PDSB_F64; };
+
+size_t dtype_size(int dt) {
+  switch (dt) {
+    case PDSB_F32: case PDSB_I32: case PDSB_U32: return 4;
+    case PDSB_F64: case PDSB_I64: case PDSB_U64: return 8;
+    case PDSB_I16: case PDSB_U16: return 2;
+    case PDSB_I8: case PDSB_U8: return 1;
+    default: return 0;  // BOOL is bit-packed
+  }
+}
+
+int64_t col_len(const pdsb_column& c) {
+  int64_t n = 0;
+  for (int i = 0; i < c.n_chunks; ++i) n += c.chunks[i].length;
+  return n;
+}
+
+int64_t chunk_nulls(const pdsb_chunk& ch) {
+  if (!ch.validity || ch.length == 0) return 0;
+  int64_t valid = 0;
+  for (int64_t i = 0; i < ch.length; ++i) {
+    int64_t b = ch.offset + i;
+    valid += (ch.validity[b >> 3] >> (b & 7)) & 1;
+  }
+  return ch.length - valid;
+}
+
+int64_t col_nulls(const pdsb_column& c) {
+  if (c.null_count >= 0) return c.null_count;
+  int64_t k = 0;
+  for (int i = 0; i < c.n_chunks; ++i) k += chunk_nulls(c.chunks[i]);
+  return k;
+}
+
+// RAII bag of stream-ordered device allocations
+struct DevBag {
+  cudaStream_t s;
+  std::vector<void*> ptrs;
+  explicit DevBag(cudaStream_t st) : s(st) {}
+  ~DevBag() { for (void* p : ptrs) dev_free(p, s); }
+  template <typename U> U* alloc(size_t count) {
+    void* p = nullptr;
+    if (dev_alloc(&p, count * sizeof(U), s)) return nullptr;
+    ptrs.push_back(p);
+    return reinterpret_cast<U*>(p);
+  }
+};
+
+// Upload one column into dst[0..n) as T.  mode: 0 null->NaN, 1 null->fill, 2 null->0
+template <typename T>
+int upload_column(const pdsb_column& c, T* dst, int mode, double fill, DevBag& bag, cudaStream_t s) {
+  int64_t off = 0;
+  for (int i = 0; i < c.n_chunks; ++i) {
+    const pdsb_chunk& ch = c.chunks[i];
+    if (ch.length == 0) continue;
+    const bool has_null = ch.validity && (c.null_count != 0) && chunk_nulls(ch) > 0;
+    if (c.dtype == DT<T>::code && !has_null) {
+      const T* src = reinterpret_cast<const T*>(ch.data) + ch.offset;
+      PDSB_CUDA_OK(cudaMemcpyAsync(dst + off, src, (size_t)ch.length * sizeof(T), cudaMemcpyHostToDevice, s));
+    } else {
+      size_t esz = dtype_size(c.dtype);
+      const uint8_t* raw;
+      size_t raw_bytes;
+      int64_t bit_off = ch.offset & 7;
+      if (c.dtype == PDSB_BOOL) {
+        raw = reinterpret_cast<const uint8_t*>(ch.data) + (ch.offset >> 3);
+        raw_bytes = (size_t)((bit_off + ch.length + 7) >> 3);
+      } else {
+        raw = reinterpret_cast<const uint8_t*>(ch.data) + (size_t)ch.offset * esz;
+        raw_bytes = (size_t)ch.length * esz;
+      }
+      uint8_t* d_raw = bag.alloc<uint8_t>(raw_bytes + 16);
+      if (!d_raw) return 1;
+      PDSB_CUDA_OK(cudaMemcpyAsync(d_raw, raw, raw_bytes, cudaMemcpyHostToDevice, s));
+      uint8_t* d_val = nullptr;
+      if (has_null) {
+        size_t vb = (size_t)((bit_off + ch.length + 7) >> 3);
+        d_val = bag.alloc<uint8_t>(vb + 16);
+        if (!d_val) return 1;
+        PDSB_CUDA_OK(cudaMemcpyAsync(d_val, ch.validity + (ch.offset >> 3), vb, cudaMemcpyHostToDevice, s));
+      }
+      if (pack_chunk<T>(d_raw, c.dtype, d_val, bit_off, ch.length, dst + off, mode, fill, s)) return 1;
+    }
+    off += ch.length;
+  }
+  return 0;
+}
+
+// rowmask[i] = 0 where column c is null
+template <typename T>
+int mask_column(const pdsb_column& c, T* rowmask, DevBag& bag, cudaStream_t s) {
+  int64_t off = 0;
+  for (int i = 0; i < c.n_chunks; ++i) {
+    const pdsb_chunk& ch = c.chunks[i];
+    if (ch.length && ch.validity && chunk_nulls(ch) > 0) {
+      int64_t bit_off = ch.offset & 7;
+      size_t vb = (size_t)((bit_off + ch.length + 7) >> 3);
+      uint8_t* d_val = bag.alloc<uint8_t>(vb + 16);
+      if (!d_val) return 1;
+      PDSB_CUDA_OK(cudaMemcpyAsync(d_val, ch.validity + (ch.offset >> 3), vb, cudaMemcpyHostToDevice, s));
+      if (and_validity<T>(d_val, bit_off, ch.length, rowmask + off, s)) return 1;
+    }
+    off += ch.length;
+  }
+  return 0;
+}
+
+inline int64_t pad_ld(int64_t n) { return (n + 31) & ~int64_t(31); }   // 128-byte aligned columns
+
+struct ResultOwner { std::vector<void*> pinned; };
+
+void* result_buf(pdsb_host_result* r, size_t bytes) {
+  if (!r->_owner) r->_owner = new ResultOwner();
+  void* p = pinned_alloc(bytes ? bytes : 8);
+  if (p) reinterpret_cast<ResultOwner*>(r->_owner)->pinned.push_back(p);
+  return p;
+}
+
+template <typename T>
+int moments_any(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, const T* mask, int64_t n, int p, int t,
+                double* M, cudaStream_t s);
+template <> int moments_any<float>(const float* X, int64_t ldx, const float* Y, int64_t ldy, const float* w,
+                                   const float* mask, int64_t n, int p, int t, double* M, cudaStream_t s) {
+  return pdsb_dev_moments_f32(X, ldx, Y, ldy, w, mask, n, p, t, M, s);
+}
+template <> int moments_any<double>(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w,
+                                    const double* mask, int64_t n, int p, int t, double* M, cudaStream_t s) {
+  return pdsb_dev_moments_f64(X, ldx, Y, ldy, w, mask, n, p, t, M, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Shared front end: null policy + upload of [targets | features] (+ weights) into the device frame.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+struct Frame {
+  T* Z = nullptr;       // [ld x (t + p)] column-major: targets first, then features
+  int64_t ld = 0, n = 0;
+  int p = 0, t = 0;
+  T* mask = nullptr;    // per-row validity (nullptr: every row valid)
+  T* w = nullptr;
+  bool any_null = false;
+  const T* Y() const { return Z; }
+  const T* X() const { return Z + (size_t)t * ld; }
+};
+
+// online = rolling/recursive: rows are never dropped, nulls become NaN (or the fill value) and the kernel masks them
+template <typename T>
+int build_frame(const pdsb_column* cols, int n_cols, int n_targets, const pdsb_column* wcol, const NullPolicy& pol,
+                bool multi, bool online, Frame<T>& F, DevBag& bag, cudaStream_t s) {
+  if (n_cols < n_targets + 1) { set_error("Data is empty"); return 1; }
+  const int64_t n = col_len(cols[0]);
+  for (int c = 1; c < n_cols; ++c)
+    if (col_len(cols[c]) != n) { set_error("Seires don't have the same length."); return 1; }
+  F.n = n; F.t = n_targets; F.p = n_cols - n_targets; F.ld = pad_ld(n > 0 ? n : 1);
+  bool y_null = false, x_null = false;
+  for (int c = 0; c < n_targets; ++c) y_null |= col_nulls(cols[c]) > 0;
+  for (int c = n_targets; c < n_cols; ++c) x_null |= col_nulls(cols[c]) > 0;
+  F.any_null = y_null || x_null;
+  if (n == 0) { set_error("Empty data"); return 1; }
+  bool need_mask = false;
+  std::vector<int> mode(n_cols, 0);
+  std::vector<int> masks(n_cols, 0);      // 1: nulls of this column drop the row
+  double fill = pol.fill;
+  if (F.any_null) {
+    if (multi) {   // series_to_mat_for_multi_lr, linear_regression.rs:301-332
+      if (pol.kind == NullKind::RAISE) { set_error("Nulls found in data"); return 1; }
+      if (pol.kind != NullKind::FILL) { set_error("The null policy is not supported by multi-target linear regression."); return 1; }
+      if (y_null) { set_error("Filling null doesn't work for multi-target lstsq when there are nulls in any of the targets."); return 1; }
+      for (int c = n_targets; c < n_cols; ++c) mode[c] = 1;
+    } else {
+      switch (pol.kind) {
+        case NullKind::RAISE: set_error("Nulls found in data"); return 1;
+        case NullKind::IGNORE: case NullKind::SKIP_WINDOW: break;   // null -> NaN
+        case NullKind::SKIP:
+          if (online) break;                                        // rows kept as NaN, kernel skips them
+          need_mask = true;
+          for (int c = 0; c < n_cols; ++c) { mode[c] = 2; masks[c] = 1; }
+          break;
+        case NullKind::FILL: case NullKind::FILL_WINDOW:
+          for (int c = n_targets; c < n_cols; ++c) mode[c] = 1;
+          if (y_null && !online && pol.kind == NullKind::FILL) { need_mask = true; mode[0] = 2; masks[0] = 1; }
+          break;
+      }
+    }
+  }
+  F.Z = bag.alloc<T>((size_t)F.ld * n_cols);
+  if (!F.Z) return 1;
+  for (int c = 0; c < n_cols; ++c)
+    if (upload_column<T>(cols[c], F.Z + (size_t)c * F.ld, mode[c], fill, bag, s)) return 1;
+  if (need_mask) {
+    F.mask = bag.alloc<T>((size_t)F.ld);
+    if (!F.mask) return 1;
+    if (fill_value<T>(F.mask, n, T(1), s)) return 1;
+    for (int c = 0; c < n_cols; ++c)
+      if (masks[c] && mask_column<T>(cols[c], F.mask, bag, s)) return 1;
+    for (int c = 0; c < n_cols; ++c)
+      if (zero_masked<T>(F.Z + (size_t)c * F.ld, F.mask, n, s)) return 1;
+  }
+  if (wcol) {
+    if (col_len(*wcol) != n) { set_error("Shape of weights is not the same as the data."); return 1; }
+    F.w = bag.alloc<T>((size_t)F.ld);
+    if (!F.w) return 1;
+    if (upload_column<T>(*wcol, F.w, 0, 0.0, bag, s)) return 1;
+  }
+  return 0;
+}
+
+template <typename T>
+int host_lin_reg_t(const pdsb_column* cols, int n_cols, const pdsb_lr_kwargs* kw, int n_targets, int want_pred,
+                   int w_rcond, pdsb_host_result* out) {
+  cudaStream_t s, s2;
+  if (thread_streams(&s, &s2)) return 1;
+  NullPolicy pol;
+  if (parse_null_policy(kw->null_policy, &pol)) return 1;
+  const bool multi = n_targets > 1;
+  const bool weighted = kw->weighted && !multi && !w_rcond;
+  const pdsb_column* wcol = weighted ? &cols[0] : nullptr;
+  const pdsb_column* data = weighted ? cols + 1 : cols;
+  const int n_data = weighted ? n_cols - 1 : n_cols;
+  DevBag bag(s);
+  Frame<T> F;
+  if (build_frame<T>(data, n_data, n_targets, wcol, pol, multi, false, F, bag, s)) return 1;
+  const int p = F.p, t = F.t;
+  const int add_bias = kw->bias ? 1 : 0;
+  const int q = p + add_bias;
+  if (p < 1) { set_error("Data is empty"); return 1; }
+  if (!multi && !F.mask && F.n < q) { set_error("#Data < #features. No conclusive result."); return 1; }
+
+  pdsb_solve_opts o{};
+  o.p = p; o.t = t; o.add_bias = add_bias; o.solver = solver_from_string(kw->solver);
+  o.l1_reg = kw->l1_reg; o.l2_reg = kw->l2_reg; o.tol = kw->tol; o.singular_x_tol = kw->singular_x_tol;
+  o.positive = kw->positive; o.max_iter = (int)kw->max_iter;
+  const bool is_f32 = sizeof(T) == 4;
+  if (w_rcond) {
+    o.method = PDSB_METHOD_RCOND;
+    const double eps = is_f32 ? (double)FLT_EPSILON : DBL_EPSILON;
+    double rc = is_f32 ? (double)(float)kw->tol : kw->tol;
+    o.tol = std::max(rc, eps * (double)std::max<int64_t>(F.n, q));
+    o.singular_x_tol = 0.0;
+  } else if (weighted) {
+    o.method = PDSB_METHOD_LSTSQ; o.l2_reg = 0.0; o.singular_x_tol = 0.0;   // faer_weighted_lr: no ridge, no gate
+  } else if (multi) {
+    o.method = PDSB_METHOD_LSTSQ; o.l1_reg = 0.0;
+  } else {
+    const bool l1 = kw->l1_reg > 0.0, l2 = kw->l2_reg > 0.0;
+    if (!l1 && !kw->positive) o.method = PDSB_METHOD_LSTSQ;
+    else if (!l1 && !l2 && kw->positive) { o.method = PDSB_METHOD_NNLS; if (is_f32) o.max_iter = want_pred ? 2000 : 200; }
+    else {
+      o.method = PDSB_METHOD_CD;
+      if (!l1) { o.l1_reg = 0.0; o.positive = 1; }
+      if (is_f32) o.max_iter = 2000;
+    }
+  }
+  const int q1 = p + t + 1;
+  double* dM = bag.alloc<double>((size_t)q1 * q1);
+  double* dbeta = bag.alloc<double>((size_t)q * t);
+  double* daux = bag.alloc<double>((size_t)q * q + q);
+  int* dstatus = bag.alloc<int>(4);
+  if (!dM || !dbeta || !daux || !dstatus) return 1;
+  if (moments_any<T>(F.X(), F.ld, F.Y(), F.ld, F.w, F.mask, F.n, p, t, dM, s)) return 1;
+  if (solve_from_moments(dM, o, dbeta, dstatus, w_rcond ? daux : nullptr, s)) return 1;
+
+  std::vector<double> hbeta((size_t)q * t), haux(q);
+  int hstatus = 0;
+  double hcount = 0.0;
+  PDSB_CUDA_OK(cudaMemcpyAsync(hbeta.data(), dbeta, hbeta.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  PDSB_CUDA_OK(cudaMemcpyAsync(&hstatus, dstatus, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PDSB_CUDA_OK(cudaMemcpyAsync(&hcount, dM + (size_t)q1 * q1 - 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (w_rcond) PDSB_CUDA_OK(cudaMemcpyAsync(haux.data(), daux, q * sizeof(double), cudaMemcpyDeviceToHost, s));
+
+  T* dpred = nullptr; T* dresid = nullptr; uint8_t* dvalid = nullptr;
+  if (want_pred) {
+    dpred = bag.alloc<T>((size_t)F.ld * t);
+    dresid = bag.alloc<T>((size_t)F.ld * t);
+    dvalid = bag.alloc<uint8_t>((size_t)F.ld);
+    if (!dpred || !dresid || !dvalid) return 1;
+    if (predict_resid<T>(F.X(), F.ld, F.Y(), F.ld, nullptr, F.mask, F.n, p, t, add_bias, dbeta, dstatus, dpred, dresid,
+                         F.ld, dvalid, nullptr, s)) return 1;
+  }
+  PDSB_CUDA_OK(cudaStreamSynchronize(s));
+  if (F.mask) {
+    const int64_t n_valid = (int64_t)llround(hcount);
+    if (!multi && n_valid < q) { set_error("#Data < #features. No conclusive result."); return 1; }
+    if (weighted && n_valid != F.n) { set_error("Shape of weights is not the same as the data."); return 1; }
+  }
+  memset(out, 0, sizeof(*out));
+  out->is_f32 = is_f32; out->n_coef = q; out->n_targets = t; out->gated = hstatus != 0; out->n_rows = want_pred ? F.n : 0;
+  if (!want_pred) {
+    T* c = reinterpret_cast<T*>(result_buf(out, (size_t)q * t * sizeof(T)));
+    if (!c) return 1;
+    for (size_t i = 0; i < (size_t)q * t; ++i) c[i] = (T)hbeta[i];
+    out->coeffs = c;
+    if (w_rcond) {
+      T* sv = reinterpret_cast<T*>(result_buf(out, (size_t)q * sizeof(T)));
+      if (!sv) return 1;
+      for (int i = 0; i < q; ++i) sv[i] = (T)haux[i];
+      out->singular_values = sv;
+    }
+    return 0;
+  }
+  T* hp = reinterpret_cast<T*>(result_buf(out, (size_t)F.n * t * sizeof(T)));
+  T* hr = reinterpret_cast<T*>(result_buf(out, (size_t)F.n * t * sizeof(T)));
+  if (!hp || !hr) return 1;
+  for (int k = 0; k < t; ++k) {
+    PDSB_CUDA_OK(cudaMemcpyAsync(hp + (size_t)k * F.n, dpred + (size_t)k * F.ld, (size_t)F.n * sizeof(T), cudaMemcpyDeviceToHost, s));
+    PDSB_CUDA_OK(cudaMemcpyAsync(hr + (size_t)k * F.n, dresid + (size_t)k * F.ld, (size_t)F.n * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+  if (F.mask || hstatus != 0) {
+    uint8_t* hv = reinterpret_cast<uint8_t*>(result_buf(out, (size_t)F.n));
+    if (!hv) return 1;
+    PDSB_CUDA_OK(cudaMemcpyAsync(hv, dvalid, (size_t)F.n, cudaMemcpyDeviceToHost, s));
+    out->valid = hv;
+  }
+  PDSB_CUDA_OK(cudaStreamSynchronize(s));
+  out->pred = hp; out->resid = hr;
+  return 0;
+}
+
+template <typename T>
+int host_report_t(const pdsb_column* cols, int n_cols, const pdsb_lr_kwargs* kw, int weighted, pdsb_host_result* out) {
+  cudaStream_t s, s2;
+  if (thread_streams(&s, &s2)) return 1;
+  NullPolicy pol;
+  if (parse_null_policy(kw->null_policy, &pol)) return 1;
+  const int skip = weighted ? 2 : 1;       // [w] var y x...
+  if (n_cols < skip + 2) { set_error("Data is empty"); return 1; }
+  const pdsb_column& vc = cols[skip - 1];
+  double y_var = NAN;
+  if (col_len(vc) > 0 && vc.n_chunks > 0) {
+    const pdsb_chunk& ch = vc.chunks[0];
+    bool valid = !ch.validity || ((ch.validity[ch.offset >> 3] >> (ch.offset & 7)) & 1);
+    if (valid && ch.length > 0) {
+      if (vc.dtype == PDSB_F64) y_var = reinterpret_cast<const double*>(ch.data)[ch.offset];
+      else if (vc.dtype == PDSB_F32) y_var = reinterpret_cast<const float*>(ch.data)[ch.offset];
+    }
+  }
+  DevBag bag(s);
+  Frame<T> F;
+  if (build_frame<T>(cols + skip, n_cols - skip, 1, weighted ? &cols[0] : nullptr, pol, false, false, F, bag, s)) return 1;
+  const int add_bias = kw->bias ? 1 : 0;
+  const int q = F.p + add_bias;
+  if (!F.mask && F.n < q) { set_error("#Data < #features. No conclusive result."); return 1; }
+  double* dout = bag.alloc<double>((size_t)8 * q);
+  if (!dout) return 1;
+  const int se = weighted ? 0 : se_type_from_string(kw->std_err);
+  if (report_stats<T>(F.X(), F.ld, F.Y(), F.w, F.mask, F.n, F.p, add_bias, se, y_var, dout, s)) return 1;
+  memset(out, 0, sizeof(*out));
+  out->is_f32 = sizeof(T) == 4; out->n_coef = q; out->n_targets = 1;
+  out->report = reinterpret_cast<double*>(result_buf(out, (size_t)8 * q * sizeof(double)));
+  if (!out->report) return 1;
+  PDSB_CUDA_OK(cudaMemcpyAsync(out->report, dout, (size_t)8 * q * sizeof(double), cudaMemcpyDeviceToHost, s));
+  PDSB_CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+template <typename T>
+int host_online_t(const pdsb_column* cols, int n_cols, const pdsb_lr_kwargs* kw, int rolling, pdsb_host_result* out) {
+  cudaStream_t s, s2;
+  if (thread_streams(&s, &s2)) return 1;
+  NullPolicy pol;
+  if (parse_null_policy(kw->null_policy, &pol)) return 1;
+  if (rolling) {   // linear_regression.rs:1214-1219
+    if (pol.kind == NullKind::SKIP) pol.kind = NullKind::SKIP_WINDOW;
+    else if (pol.kind == NullKind::FILL) pol.kind = NullKind::FILL_WINDOW;
+  }
+  DevBag bag(s);
+  Frame<T> F;
+  if (build_frame<T>(cols, n_cols, 1, nullptr, pol, false, true, F, bag, s)) return 1;
+  const int add_bias = kw->bias ? 1 : 0;
+  const int q = F.p + add_bias;
+  if (F.n < q) { set_error("#Data < #features. No conclusive result."); return 1; }
+  if (kw->n < 1) { set_error("window / start_with must be >= 1"); return 1; }
+  if (kw->n > F.n) { set_error("#Data < window size. No conclusive result."); return 1; }
+  bool y_null = col_nulls(cols[0]) > 0;
+  int skip = 0;
+  if (F.any_null) {
+    if (rolling) skip = (pol.kind == NullKind::SKIP_WINDOW) || (pol.kind == NullKind::FILL_WINDOW && y_null);
+    else skip = (pol.kind == NullKind::SKIP) || (pol.kind == NullKind::FILL && y_null);
+  }
+  T* dco = bag.alloc<T>((size_t)F.n * q);
+  T* dpr = bag.alloc<T>((size_t)F.n);
+  uint8_t* dva = bag.alloc<uint8_t>((size_t)F.n);
+  if (!dco || !dpr || !dva) return 1;
+  const int64_t window = rolling ? kw->n : 0;
+  const int64_t min_rows = rolling ? kw->min_size : kw->n;
+  if (online_lin_reg<T>(F.X(), F.ld, F.Y(), F.n, F.p, add_bias, window, min_rows, skip, kw->lambda, dco, dpr, dva, s)) return 1;
+  memset(out, 0, sizeof(*out));
+  out->is_f32 = sizeof(T) == 4; out->n_coef = q; out->n_targets = 1; out->n_rows = F.n;
+  out->coeffs = result_buf(out, (size_t)F.n * q * sizeof(T));
+  out->pred = result_buf(out, (size_t)F.n * sizeof(T));
+  out->valid = reinterpret_cast<uint8_t*>(result_buf(out, (size_t)F.n));
+  if (!out->coeffs || !out->pred || !out->valid) return 1;
+  PDSB_CUDA_OK(cudaMemcpyAsync(out->coeffs, dco, (size_t)F.n * q * sizeof(T), cudaMemcpyDeviceToHost, s));
+  PDSB_CUDA_OK(cudaMemcpyAsync(out->pred, dpr, (size_t)F.n * sizeof(T), cudaMemcpyDeviceToHost, s));
+  PDSB_CUDA_OK(cudaMemcpyAsync(out->valid, dva, (size_t)F.n, cudaMemcpyDeviceToHost, s));
+  PDSB_CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+template <typename T>
+int host_grouped_t(const pdsb_column* cols, int n_cols, const int64_t* offsets, int64_t n_groups,
+                   const pdsb_lr_kwargs* kw, pdsb_host_result* out) {
+  cudaStream_t s, s2;
+  if (thread_streams(&s, &s2)) return 1;
+  NullPolicy pol;
+  if (parse_null_policy(kw->null_policy, &pol)) return 1;
+  DevBag bag(s);
+  Frame<T> F;
+  // nulls: only "skip" maps onto the batched kernel (row -> NaN -> dropped inside its group)
+  for (int c = 0; c < n_cols; ++c)
+    if (col_nulls(cols[c]) > 0 && pol.kind != NullKind::SKIP) {
+      if (pol.kind == NullKind::RAISE) set_error("Nulls found in data");
+      else set_error("grouped lin_reg: only null_policy='skip' is supported with nulls");
+      return 1;
+    }
+  NullPolicy nanpol{NullKind::IGNORE, 0.0};
+  if (build_frame<T>(cols, n_cols, 1, nullptr, nanpol, false, true, F, bag, s)) return 1;
+  if (n_groups < 1 || offsets[0] != 0 || offsets[n_groups] != F.n) { set_error("grouped lin_reg: bad group offsets"); return 1; }
+  const int add_bias = kw->bias ? 1 : 0;
+  const int q = F.p + add_bias;
+  pdsb_solve_opts o{};
+  o.p = F.p; o.t = 1; o.add_bias = add_bias; o.method = PDSB_METHOD_LSTSQ; o.solver = solver_from_string(kw->solver);
+  o.l2_reg = kw->l2_reg; o.singular_x_tol = kw->singular_x_tol;
+  if (kw->l1_reg > 0.0 || kw->positive) { set_error("grouped lin_reg: only OLS / ridge is batched"); return 1; }
+  int64_t* doff = bag.alloc<int64_t>((size_t)n_groups + 1);
+  double* dbeta = bag.alloc<double>((size_t)n_groups * q);
+  int* dst = bag.alloc<int>((size_t)n_groups);
+  if (!doff || !dbeta || !dst) return 1;
+  PDSB_CUDA_OK(cudaMemcpyAsync(doff, offsets, (size_t)(n_groups + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  if (grouped_lin_reg<T>(F.X(), F.ld, F.Y(), doff, n_groups, F.n, F.p, o, dbeta, dst, s)) return 1;
+  std::vector<double> hb((size_t)n_groups * q);
+  std::vector<int> hs((size_t)n_groups);
+  PDSB_CUDA_OK(cudaMemcpyAsync(hb.data(), dbeta, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  PDSB_CUDA_OK(cudaMemcpyAsync(hs.data(), dst, hs.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+  PDSB_CUDA_OK(cudaStreamSynchronize(s));
+  memset(out, 0, sizeof(*out));
+  out->is_f32 = sizeof(T) == 4; out->n_coef = q; out->n_targets = 1; out->n_rows = n_groups;
+  T* c = reinterpret_cast<T*>(result_buf(out, (size_t)n_groups * q * sizeof(T)));
+  uint8_t* v = reinterpret_cast<uint8_t*>(result_buf(out, (size_t)n_groups));
+  if (!c || !v) return 1;
+  for (size_t i = 0; i < hb.size(); ++i) c[i] = (T)hb[i];
+  for (int64_t g = 0; g < n_groups; ++g) v[g] = hs[g] == 0;
+  out->coeffs = c; out->valid = v;
+  return 0;
+}
+
+}  // namespace
+}  // namespace pdsb
+
+using namespace pdsb;
+
+extern "C" {
+
+void pdsb_host_result_free(pdsb_host_result* r) {
+  if (!r || !r->_owner) return;
+  ResultOwner* o = reinterpret_cast<ResultOwner*>(r->_owner);
+  for (void* p : o->pinned) pinned_free(p);
+  delete o;
+  memset(r, 0, sizeof(*r));
+}
+
+#define PDSB_GUARD(call)                                    \
+  do {                                                      \
+    if (require_device()) return 1;                         \
+    if (!kw || !cols || !out) { set_error("null argument"); return 1; } \
+    memset(out, 0, sizeof(*out));                           \
+    int rc = (call);                                        \
+    if (rc) pdsb_host_result_free(out);                     \
+    return rc;                                              \
+  } while (0)
+
+int pdsb_host_lin_reg(const pdsb_column* cols, int n_cols, const pdsb_lr_kwargs* kw, int f32, int n_targets,
+                      int want_pred, int w_rcond, pdsb_host_result* out) {
+  PDSB_GUARD(f32 ? host_lin_reg_t<float>(cols, n_cols, kw, n_targets, want_pred, w_rcond, out)
+                 : host_lin_reg_t<double>(cols, n_cols, kw, n_targets, want_pred, w_rcond, out));
+}
+int pdsb_host_report(const pdsb_column* cols, int n_cols, const pdsb_lr_kwargs* kw, int f32, int weighted,
+                     pdsb_host_result* out) {
+  PDSB_GUARD(f32 ? host_report_t<float>(cols, n_cols, kw, weighted, out)
+                 : host_report_t<double>(cols, n_cols, kw, weighted, out));
+}
+int pdsb_host_online(const pdsb_column* cols, int n_cols, const pdsb_lr_kwargs* kw, int f32, int rolling,
+                     pdsb_host_result* out) {
+  PDSB_GUARD(f32 ? host_online_t<float>(cols, n_cols, kw, rolling, out)
+                 : host_online_t<double>(cols, n_cols, kw, rolling, out));
+}
+int pdsb_host_grouped_lin_reg(const pdsb_column* cols, int n_cols, const int64_t* group_offsets, int64_t n_groups,
+                              const pdsb_lr_kwargs* kw, int f32, pdsb_host_result* out) {
+  if (!group_offsets) { set_error("null group offsets"); return 1; }
+  PDSB_GUARD(f32 ? host_grouped_t<float>(cols, n_cols, group_offsets, n_groups, kw, out)
+                 : host_grouped_t<double>(cols, n_cols, group_offsets, n_groups, kw, out));
+}
+
+}  // extern "C"

@@ -1,0 +1,363 @@
+// K5 — group_by(seg).agg(pds.lin_reg(...)) as a batched, segmented problem.
+//
+// In the reference there is no grouped code: Polars calls `_polars_plugin_pl_lr` once per group from its rayon pool
+// (/root/reference/src/utils/mod.rs:81-84 "tight group-by loops"; tests/test_linear_exprs.py:918-953).
+// Each call packs the group, builds X'X / X'y with a sequential matmul (lr_solvers.rs:186-190) and runs the gated
+// QR solve (:329-382).  Here the whole frame stays in HBM in key order and one launch sequence does all groups:
+//   pass 1  group moments: one warp per (group, chunk of <= CHUNK rows); lanes stride rows (coalesced column reads),
+//           the (p+2)(p+3)/2 moments live in registers (f32 FMA chains of <= CHUNK/32 terms -> f64 warp reduce);
+//           chunk partials are combined in a fixed order -> bit-reproducible, balanced for ragged group sizes.
+//   pass 2  batched solve: one thread per group on an interleaved (component-major) workspace so that every
+//           access is coalesced across groups: ridge, rank gate (ln|det| - sum ln diag <= ln tol), pivoted
+//           Householder QR (or Cholesky for solver="choleskey"), back-substitution.
+// HBM-bound: algorithmic bytes per row = (p+1) * s.
+#include "../common.h"
+#include "kernels.h"
+
+namespace pdsb {
+
+namespace {
+
+constexpr int CHUNK = 8192;  // rows per (group, chunk) work item
+
+// ---------------- pass 0: work list ----------------
+__global__ void count_items_kernel(const int64_t* __restrict__ offsets, int64_t n_groups, int64_t* __restrict__ item_start) {
+  // item_start[g] = number of chunks of group g (scanned on the host side of this file by a tiny kernel below)
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * blockDim.x) {
+    int64_t len = offsets[g + 1] - offsets[g];
+    item_start[g] = len > 0 ? (len + CHUNK - 1) / CHUNK : 1;
+  }
+}
+
+__global__ void scan_items_kernel(int64_t* __restrict__ item_start, int64_t n_groups) {
+  // single block exclusive scan with running carry (n_groups is at most a few million)
+  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n_groups + 1; base += blockDim.x) {
+    int64_t i = base + threadIdx.x;
+    int64_t v = (i < n_groups) ? item_start[i] : 0;
+    int64_t inc = v;
+    for (int off = 1; off < 32; off <<= 1) { int64_t y = __shfl_up_sync(0xffffffffu, inc, off); if ((threadIdx.x & 31) >= off) inc += y; }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    int64_t wpre = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wpre += warp_tot[w];
+    int64_t excl = carry + wpre + inc - v;
+    __syncthreads();
+    if (i <= n_groups) item_start[i] = excl;
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+}
+
+// ---------------- pass 1: per-(group, chunk) moments ----------------
+// Z = [x_0 .. x_{P-1}, y, 1];  Q1 = P + 2 columns; NM = Q1 (Q1+1) / 2 packed upper-triangular moments.
+template <typename T, int P>
+__global__ void __launch_bounds__(256)
+group_moments_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y,
+                     const int64_t* __restrict__ offsets, const int64_t* __restrict__ item_start,
+                     int64_t n_groups, int64_t n_items, double* __restrict__ part /* [NM][n_items] */) {
+  constexpr int Q1 = P + 2;
+  constexpr int NM = Q1 * (Q1 + 1) / 2;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t item = warp_global; item < n_items; item += nwarps) {
+    // binary search the group of this item: item_start[g] <= item < item_start[g+1]
+    int64_t lo = 0, hi = n_groups;
+    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (item_start[mid] <= item) lo = mid; else hi = mid; }
+    const int64_t g = lo;
+    const int64_t r0 = offsets[g] + (item - item_start[g]) * CHUNK;
+    const int64_t r1 = min(r0 + (int64_t)CHUNK, offsets[g + 1]);
+    T acc[NM];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) acc[k] = T(0);
+    for (int64_t r = r0 + lane; r < r1; r += 32) {
+      T z[Q1];
+#pragma unroll
+      for (int c = 0; c < P; ++c) z[c] = X[(int64_t)c * ldx + r];
+      z[P] = y[r];
+      z[P + 1] = T(1);
+      bool fin = true;   // null rows arrive as NaN (null_policy="skip"): they drop out of their group
+#pragma unroll
+      for (int c = 0; c <= P; ++c) fin = fin && isfinite(z[c]);
+      if (!fin) continue;
+      int k = 0;
+#pragma unroll
+      for (int i = 0; i < Q1; ++i)
+#pragma unroll
+        for (int j = i; j < Q1; ++j) { acc[k] = fma(z[i], z[j], acc[k]); ++k; }
+    }
+#pragma unroll
+    for (int k = 0; k < NM; ++k) {
+      double v = (double)acc[k];
+      for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) part[(size_t)k * n_items + item] = v;
+    }
+  }
+}
+
+// generic-P variant: lanes still stride rows but moments are accumulated through shared memory per warp
+template <typename T>
+__global__ void __launch_bounds__(128)
+group_moments_generic_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y,
+                             const int64_t* __restrict__ offsets, const int64_t* __restrict__ item_start,
+                             int64_t n_groups, int64_t n_items, int p, double* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int q1 = p + 2;
+  const int nm = q1 * (q1 + 1) / 2;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  T* tile = reinterpret_cast<T*>(smem_raw) + (size_t)wid * 32 * (q1 + 1);   // [32][q1+1]
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int per_lane = (nm + 31) / 32;
+  for (int64_t item = warp_global; item < n_items; item += nwarps) {
+    int64_t lo = 0, hi = n_groups;
+    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (item_start[mid] <= item) lo = mid; else hi = mid; }
+    const int64_t g = lo;
+    const int64_t r0 = offsets[g] + (item - item_start[g]) * CHUNK;
+    const int64_t r1 = min(r0 + (int64_t)CHUNK, offsets[g + 1]);
+    double acc[20];   // supports nm <= 640 (p <= 33)
+    for (int k = 0; k < 20; ++k) acc[k] = 0.0;
+    for (int64_t rb = r0; rb < r1; rb += 32) {
+      const int64_t r = rb + lane;
+      bool fin = r < r1;
+      for (int c = 0; c < q1; ++c) {
+        T v = T(0);
+        if (r < r1) v = (c < p) ? X[(int64_t)c * ldx + r] : (c == p ? y[r] : T(1));
+        fin = fin && isfinite(v);
+        tile[lane * (q1 + 1) + c] = v;
+      }
+      if (!fin) for (int c = 0; c < q1; ++c) tile[lane * (q1 + 1) + c] = T(0);
+      __syncwarp();
+      for (int m = 0; m < per_lane; ++m) {
+        int k = lane + 32 * m;
+        if (k < nm) {
+          int i = 0, rem = k;
+          while (rem >= q1 - i) { rem -= q1 - i; ++i; }
+          int j = i + rem;
+          T s = T(0);
+          for (int rr = 0; rr < 32; ++rr) s = fma(tile[rr * (q1 + 1) + i], tile[rr * (q1 + 1) + j], s);
+          acc[m] += (double)s;
+        }
+      }
+      __syncwarp();
+    }
+    for (int m = 0; m < per_lane; ++m) {
+      int k = lane + 32 * m;
+      if (k < nm) part[(size_t)k * n_items + item] = acc[m];
+    }
+  }
+}
+
+// ---------------- pass 2: batched solve, one thread per group, interleaved workspace ----------------
+struct GroupSolveArgs {
+  const double* part; const int64_t* item_start; const int64_t* offsets;
+  int64_t n_groups, n_items; int p, add_bias, solver; double l2, tol;
+  double* ws;      // [(q*q + 2q) ][n_groups]  interleaved
+  double* beta;    // [n_groups][q]
+  int* status;
+};
+
+__global__ void __launch_bounds__(128) group_solve_kernel(GroupSolveArgs a) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.n_groups) return;
+  const int p = a.p, q = p + (a.add_bias ? 1 : 0), q1 = p + 2;
+  const int64_t NG = a.n_groups;
+  double* A = a.ws + g;                                  // A(i,j) = A[(i + j*q) * NG]
+  double* b = a.ws + (size_t)q * q * NG + g;             // b(i)   = b[i * NG]
+  double* cn = a.ws + ((size_t)q * q + q) * NG + g;      // scratch q
+#define AA(i, j) A[((size_t)(i) + (size_t)(j) * q) * NG]
+#define BB(i) b[(size_t)(i) * NG]
+#define CN(i) cn[(size_t)(i) * NG]
+  // moment (i,j) of Z=[x.., y, 1], i<=j, packed index
+  auto midx = [&](int i, int j) { if (i > j) { int t = i; i = j; j = t; } return i * q1 - i * (i - 1) / 2 + (j - i); };
+  auto fz = [&](int i) { return i < p ? i : p + 1; };    // coefficient index -> Z column (bias -> ones)
+  const int64_t it0 = a.item_start[g], it1 = a.item_start[g + 1];
+  auto mom = [&](int k) { double s = 0.0; for (int64_t it = it0; it < it1; ++it) s += a.part[(size_t)k * a.n_items + it]; return s; };
+  const int64_t nrows = (int64_t)llround(mom(midx(p + 1, p + 1)));   // valid rows of the group
+  double* out = a.beta + (size_t)g * q;
+  if (nrows < q) {  // "#Data < #features" would be an error for a single call; per group it yields null
+    a.status[g] = PDSB_GATED;
+    for (int i = 0; i < q; ++i) out[i] = nan("");
+    return;
+  }
+  for (int j = 0; j < q; ++j)
+    for (int i = 0; i <= j; ++i) {
+      double v = mom(midx(fz(i), fz(j)));
+      if (i == j && i < p && a.l2 > 0.0) v += a.l2;
+      AA(i, j) = v; AA(j, i) = v;
+    }
+  for (int i = 0; i < q; ++i) BB(i) = mom(midx(fz(i), p));
+  const bool gated = a.tol > 0.0;
+  double ln_den = 0.0;
+  if (gated) {
+    for (int i = 0; i < q; ++i) {
+      double d = AA(i, i);
+      if (!(d > 0.0)) { a.status[g] = PDSB_GATED; for (int k = 0; k < q; ++k) out[k] = nan(""); return; }
+      ln_den += log(d);
+    }
+  }
+  const double ln_tol = gated ? log(a.tol) : 0.0;
+  int perm[64];
+  bool done = false;
+  if (a.solver == PDSB_SOLVER_CHOLESKEY) {
+    bool ok = true;
+    double ln_det = 0.0;
+    for (int k = 0; k < q && ok; ++k) {
+      double d = AA(k, k);
+      if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }
+      d = sqrt(d); AA(k, k) = d; ln_det += 2.0 * log(d);
+      for (int i = k + 1; i < q; ++i) AA(i, k) = AA(i, k) / d;
+      for (int j = k + 1; j < q; ++j) { double ljk = AA(j, k); for (int i = j; i < q; ++i) AA(i, j) -= AA(i, k) * ljk; }
+    }
+    if (ok) {
+      if (gated && ln_det - ln_den <= ln_tol) { a.status[g] = PDSB_GATED; for (int k = 0; k < q; ++k) out[k] = nan(""); return; }
+      for (int i = 0; i < q; ++i) { double s = BB(i); for (int j = 0; j < i; ++j) s -= AA(i, j) * BB(j); BB(i) = s / AA(i, i); }
+      for (int i = q - 1; i >= 0; --i) { double s = BB(i); for (int j = i + 1; j < q; ++j) s -= AA(j, i) * BB(j); BB(i) = s / AA(i, i); }
+      for (int i = 0; i < q; ++i) out[i] = BB(i);
+      done = true;
+    } else if (gated) {
+      a.status[g] = PDSB_GATED; for (int k = 0; k < q; ++k) out[k] = nan(""); return;
+    } else {  // restore and fall through to QR (lr_solvers.rs:288-291)
+      for (int j = 0; j < q; ++j)
+        for (int i = 0; i <= j; ++i) {
+          double v = mom(midx(fz(i), fz(j)));
+          if (i == j && i < p && a.l2 > 0.0) v += a.l2;
+          AA(i, j) = v; AA(j, i) = v;
+        }
+      for (int i = 0; i < q; ++i) BB(i) = mom(midx(fz(i), p));
+    }
+  }
+  if (!done) {
+    // Householder QR with column pivoting
+    for (int j = 0; j < q; ++j) perm[j] = j;
+    double ln_det = 0.0;
+    for (int k = 0; k < q; ++k) {
+      int piv = k; double best = -1.0;
+      for (int j = k; j < q; ++j) {
+        double s = 0.0;
+        for (int i = k; i < q; ++i) { double v = AA(i, j); s += v * v; }
+        CN(j) = s;
+        if (s > best) { best = s; piv = j; }
+      }
+      if (piv != k) {
+        for (int i = 0; i < q; ++i) { double t = AA(i, k); AA(i, k) = AA(i, piv); AA(i, piv) = t; }
+        int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+      }
+      double s = CN(piv);
+      double normx = sqrt(s), x0 = AA(k, k);
+      double alpha = (x0 >= 0.0) ? -normx : normx;
+      double v0 = x0 - alpha;
+      double vtv = v0 * v0 + (s - x0 * x0);
+      double hb = (vtv > 0.0 && isfinite(vtv)) ? 2.0 / vtv : 0.0;
+      if (hb != 0.0) {
+        for (int j = k + 1; j < q; ++j) {
+          double dot = v0 * AA(k, j);
+          for (int i = k + 1; i < q; ++i) dot += AA(i, k) * AA(i, j);
+          double f = hb * dot;
+          AA(k, j) -= f * v0;
+          for (int i = k + 1; i < q; ++i) AA(i, j) -= f * AA(i, k);
+        }
+        double dot = v0 * BB(k);
+        for (int i = k + 1; i < q; ++i) dot += AA(i, k) * BB(i);
+        double f = hb * dot;
+        BB(k) -= f * v0;
+        for (int i = k + 1; i < q; ++i) BB(i) -= f * AA(i, k);
+      }
+      AA(k, k) = alpha;
+      ln_det += log(fabs(alpha));
+    }
+    if (gated && (ln_det - ln_den <= ln_tol || isnan(ln_det))) {
+      a.status[g] = PDSB_GATED; for (int k = 0; k < q; ++k) out[k] = nan(""); return;
+    }
+    for (int i = q - 1; i >= 0; --i) {
+      double s = BB(i);
+      for (int j = i + 1; j < q; ++j) s -= AA(i, j) * BB(j);
+      double r = AA(i, i);
+      BB(i) = (r != 0.0) ? s / r : 0.0;
+    }
+    for (int i = 0; i < q; ++i) out[perm[i]] = BB(i);
+  }
+  a.status[g] = PDSB_OK;
+#undef AA
+#undef BB
+#undef CN
+}
+
+template <typename T, int P>
+int launch_moments_p(const T* X, int64_t ldx, const T* y, const int64_t* offsets, const int64_t* item_start,
+                     int64_t n_groups, int64_t n_items, double* part, cudaStream_t s) {
+  int64_t warps = n_items;
+  int grid = (int)std::min<int64_t>(ceil_div(warps, 8), (int64_t)sm_count() * 16);
+  if (grid < 1) grid = 1;
+  group_moments_kernel<T, P><<<grid, 256, 0, s>>>(X, ldx, y, offsets, item_start, n_groups, n_items, part);
+  PDSB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+
+template <typename T>
+int grouped_lin_reg(const T* X, int64_t ldx, const T* y, const int64_t* offsets, int64_t n_groups, int64_t n,
+                    int p, const pdsb_solve_opts& o, double* beta, int* status, cudaStream_t s) {
+  if (n_groups <= 0) return 0;
+  if (o.method != PDSB_METHOD_LSTSQ) { set_error("grouped lin_reg: only OLS / ridge is batched"); return 1; }
+  const int q = p + (o.add_bias ? 1 : 0);
+  if (p < 1 || p > 33 || q > 64) { set_error("grouped lin_reg: p=%d not supported (1..33)", p); return 1; }
+  const int q1 = p + 2, nm = q1 * (q1 + 1) / 2;
+  // work list: we need n_items on the host to size the partial buffer -> one small D2H
+  int64_t* item_start = nullptr;
+  if (dev_alloc((void**)&item_start, (size_t)(n_groups + 1) * sizeof(int64_t), s)) return 1;
+  count_items_kernel<<<(int)std::min<int64_t>(ceil_div(n_groups, 256), 1024), 256, 0, s>>>(offsets, n_groups, item_start);
+  count_launch();
+  scan_items_kernel<<<1, 1024, 0, s>>>(item_start, n_groups);
+  count_launch();
+  int64_t n_items = 0;
+  PDSB_CUDA_OK(cudaMemcpyAsync(&n_items, item_start + n_groups, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  PDSB_CUDA_OK(cudaStreamSynchronize(s));
+  double* part = nullptr;
+  if (dev_alloc((void**)&part, (size_t)nm * n_items * sizeof(double), s)) { dev_free(item_start, s); return 1; }
+  int rc = 0;
+#define CASE_P(PP) case PP: rc = launch_moments_p<T, PP>(X, ldx, y, offsets, item_start, n_groups, n_items, part, s); break;
+  switch (p) {
+    CASE_P(1) CASE_P(2) CASE_P(3) CASE_P(4) CASE_P(5) CASE_P(6) CASE_P(7) CASE_P(8) CASE_P(9) CASE_P(10)
+    default: {
+      size_t smem = (size_t)4 * 32 * (q1 + 1) * sizeof(T);
+      int grid = (int)std::min<int64_t>(ceil_div(n_items, 4), (int64_t)sm_count() * 16);
+      if (grid < 1) grid = 1;
+      group_moments_generic_kernel<T><<<grid, 128, smem, s>>>(X, ldx, y, offsets, item_start, n_groups, n_items, p, part);
+      cudaError_t e = cudaGetLastError();
+      count_launch();
+      if (e != cudaSuccess) { set_error("group moments launch failed: %s", cudaGetErrorString(e)); rc = 1; }
+    }
+  }
+#undef CASE_P
+  double* ws = nullptr;
+  if (!rc && dev_alloc((void**)&ws, ((size_t)q * q + 2 * q) * n_groups * sizeof(double), s)) rc = 1;
+  if (!rc) {
+    GroupSolveArgs a;
+    a.part = part; a.item_start = item_start; a.offsets = offsets; a.n_groups = n_groups; a.n_items = n_items;
+    a.p = p; a.add_bias = o.add_bias; a.solver = o.solver; a.l2 = o.l2_reg; a.tol = o.singular_x_tol;
+    a.ws = ws; a.beta = beta; a.status = status;
+    group_solve_kernel<<<(int)ceil_div(n_groups, 128), 128, 0, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    count_launch();
+    if (e != cudaSuccess) { set_error("group solve launch failed: %s", cudaGetErrorString(e)); rc = 1; }
+  }
+  if (ws) dev_free(ws, s);
+  dev_free(part, s);
+  dev_free(item_start, s);
+  (void)n;
+  return rc;
+}
+
+template int grouped_lin_reg<float>(const float*, int64_t, const float*, const int64_t*, int64_t, int64_t, int,
+                                    const pdsb_solve_opts&, double*, int*, cudaStream_t);
+template int grouped_lin_reg<double>(const double*, int64_t, const double*, const int64_t*, int64_t, int64_t, int,
+                                     const pdsb_solve_opts&, double*, int*, cudaStream_t);
+
+}  // namespace pdsb
