@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric: pds.lin_reg rows/sec on 1e8 x 32 f32, return_pred=True (configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--rows R] [--features P] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic rows: moments (K2) -> solve (K3) ->
+predict/residual (K4).  Prints ONE JSON line (rank 0):
+
+  value      whole-job rows/s with the frame already resident in HBM (CUDA events, max over ranks)
+  e2e        the same metric through the reference-facing plugin symbol `_polars_plugin_pl_lr_pred_f32` with HOST
+             (pinned) Arrow buffers: H2D of the 33 columns and D2H of pred+resid are inside the timed region
+  roofline   the dominant kernel (the Gram/moments kernel) timed alone with CUDA events; algorithmic bytes =
+             (p + 1) * 4 per row against the measured HBM peak in MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle ("port" of the reference, numpy/OpenBLAS with all host threads) on a bounded sample
+
+N > 1 (torchrun): rows are sharded, every rank owns `--rows` rows (weak scaling); per step each rank builds its
+partial moments, ONE NCCL all-reduce sums the (p+2)^2 f64 moments, every rank solves redundantly and predicts its
+shard.  `--impl reference` times the oracle port on the host cores (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU")
+    ap.add_argument("--features", type=int, default=32)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-rows", type=int, default=8_000_000, help="bounded CPU-baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [x.strip() for x in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_on_device(torch, rows, p, seed, device):
+    """X ~ N(0,1), beta_j = ((j mod 7) - 3)/4, y = X beta + 0.1 N(0,1)  (seed 208 as the reference's
+    benchmarks/test_linear_regression.py:9).  Column-major: tensor (p, ld)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    ld = (rows + 31) // 32 * 32
+    X = torch.empty((p, ld), dtype=torch.float32, device=device)
+    y = torch.zeros((1, ld), dtype=torch.float32, device=device)
+    beta = ((torch.arange(p, device=device) % 7).float() - 3.0) / 4.0
+    chunk = 1 << 24
+    for c in range(p):
+        X[c].normal_(generator=g)
+    for s in range(0, ld, chunk):
+        e = min(ld, s + chunk)
+        y[0, s:e] = beta @ X[:, s:e]
+    noise = torch.empty(ld, dtype=torch.float32, device=device).normal_(generator=g)
+    y[0] += 0.1 * noise
+    del noise
+    return X, y, ld
+
+
+def cpu_baseline(rows, p, steps=1):
+    """The oracle port (numpy/OpenBLAS, all host threads) on a bounded sample of the same workload."""
+    from oracle import lin_reg_oracle as orc
+
+    rng = np.random.default_rng(208)
+    X = rng.standard_normal((p, rows), dtype=np.float32)
+    beta = ((np.arange(p) % 7) - 3.0) / 4.0
+    y = (beta.astype(np.float32) @ X + 0.1 * rng.standard_normal(rows, dtype=np.float32)).astype(np.float32)
+    cols = [orc.Col("y", y)] + [orc.Col(f"x{i}", X[i]) for i in range(p)]
+    kw = {"bias": False, "null_policy": "skip", "l1_reg": 0.0, "l2_reg": 0.0, "solver": "qr", "tol": 1e-5,
+          "max_iter": 200, "weighted": False, "positive": False, "singular_x_tol": 1e-6}
+    orc.pl_lr_pred(cols[:], kw, f32=True)  # warm-up (BLAS threads, page faults)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = orc.pl_lr_pred(cols, kw, f32=True)
+    dt = (time.perf_counter() - t0) / steps
+    assert out["pred"][0].shape[0] == rows
+    return rows / dt, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    rows = args.cpu_rows
+    v, dt = cpu_baseline(rows, args.features, steps=max(1, min(args.steps, 3)))
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "lin_reg rows/sec (f32, return_pred=True)", "value": v, "unit": "rows/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"pds.lin_reg {args.rows:.0e} x {args.features} f32, return_pred=True (configs[1]); "
+                               f"CPU arm timed on a {rows}-row sample"},
+        "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port",
+                         "sample": f"{rows} rows x {args.features} f32 through oracle.pl_lr_pred (numpy/OpenBLAS)"},
+        "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from polars_ds_extension_b200 import device as dev
+    from polars_ds_extension_b200._lib import lib, METHOD_LSTSQ
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    n_gpus = world
+    rows, p = args.rows, args.features
+    L = lib()
+
+    X, y, ld = synth_on_device(torch, rows, p, 208 + rank, device)
+    q1 = p + 2
+    M = torch.empty((q1, q1), dtype=torch.float64, device=device)
+    beta = torch.empty((1, p), dtype=torch.float64, device=device)
+    status = torch.zeros(4, dtype=torch.int32, device=device)
+    pred = torch.empty((1, ld), dtype=torch.float32, device=device)
+    resid = torch.empty((1, ld), dtype=torch.float32, device=device)
+    tol = 1e-6  # default singular_x_tol of the f32 family (expr_linear.py:184-186)
+
+    def step():
+        dev.moments(X, y, n=rows, out=M)
+        if world > 1:
+            dist.all_reduce(M)  # the only exchange of the row-sharded path: (p+2)^2 f64 partial moments
+        dev.solve(M, p, 1, add_bias=False, method=METHOD_LSTSQ, singular_x_tol=tol, beta=beta, status=status)
+        dev.predict(X, y, beta, status, add_bias=False, n=rows, pred=pred, resid=resid)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = dev.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    launches = dev.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = rows * n_gpus * args.steps / (ms * 1e-3)
+    path = int(L.pdsb_last_moments_path())
+
+    # ---- roofline of the dominant kernel (moments), timed alone ----
+    for _ in range(3):
+        dev.moments(X, y, n=rows, out=M)
+    torch.cuda.synchronize()
+    reps = max(args.steps, 5)
+    ev0.record()
+    for _ in range(reps):
+        dev.moments(X, y, n=rows, out=M)
+    ev1.record()
+    torch.cuda.synchronize()
+    k_ms = ev0.elapsed_time(ev1) / reps
+    alg_bytes = rows * (p + 1) * 4
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    # coefficients sanity inside the bench: parity against the generating beta (noise 0.1 => tiny error at 1e8 rows)
+    bt = ((np.arange(p) % 7) - 3.0) / 4.0
+    coef_err = float(np.max(np.abs(beta.cpu().numpy()[0] - bt)))
+
+    e2e = None
+    if rank == 0 and not args.no_e2e:
+        e2e = run_e2e(torch, X, y, rows, p, args)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu and n_gpus == 1:
+        v, dt = cpu_baseline(args.cpu_rows, p)
+        cpu = {"value": v, "unit": "rows/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{args.cpu_rows} rows x {p} f32 through oracle.pl_lr_pred (numpy/OpenBLAS, all threads), {dt:.2f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "lin_reg rows/sec (f32, return_pred=True)", "value": value, "unit": "rows/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"pds.lin_reg {rows} rows x {p} f32 features per GPU, add_bias=False, return_pred=True "
+                                   f"(BASELINE configs[1]); step = moments + solve + predict/resid",
+                       "rows_per_gpu": rows, "features": p,
+                       "parallelism": f"row-sharded x{n_gpus}, one f64 moments all-reduce per step" if n_gpus > 1 else "single GPU",
+                       "l2_policy": "inputs (13.2 GB per step) are larger than L2; no explicit flush",
+                       "moments_kernel": "tcgen05+TMA 3xTF32" if path == 1 else "simt f32 (f64 accumulate)",
+                       "max_abs_coef_error_vs_generating_beta": coef_err},
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "moments (Gram X'X | X'y)", "kernel_ms": k_ms,
+                         "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(torch, X, y, rows, p, args):
+    """Through the plugin C ABI with host buffers: what a Polars user of the drop-in library would time."""
+    import pyarrow as pa
+
+    from polars_ds_extension_b200 import _harness
+
+    try:
+        host = torch.empty((p + 1, rows), dtype=torch.float32, pin_memory=True)
+    except Exception as e:  # not enough lockable host memory
+        return {"value": None, "unit": "rows/s", "error": f"pinned allocation failed: {e}"}
+    host[0].copy_(y[0, :rows])
+    for c in range(p):
+        host[c + 1].copy_(X[c, :rows])
+    torch.cuda.synchronize()
+    hn = host.numpy()
+    inputs = [pa.array(hn[i]) for i in range(p + 1)]          # zero-copy views of the pinned buffers
+    names = ["y"] + [f"x{i}" for i in range(p)]
+    kw = {"bias": False, "null_policy": "skip", "l1_reg": 0.0, "l2_reg": 0.0, "solver": "qr", "tol": 1e-5,
+          "max_iter": 200, "weighted": False, "positive": False, "singular_x_tol": 1e-6}
+    res = _harness.call_plugin("pl_lr_pred_f32", inputs, names, kw)   # warm-up (pinned result pool, allocator)
+    del res
+    res = _harness.call_plugin("pl_lr_pred_f32", inputs, names, kw)
+    del res
+    torch.cuda.synchronize()
+    k = max(1, args.e2e_steps)
+    t0 = time.perf_counter()
+    for _ in range(k):
+        res = _harness.call_plugin("pl_lr_pred_f32", inputs, names, kw)
+        assert len(res) == rows
+        del res
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / k
+    return {"value": rows / dt, "unit": "rows/s", "h2d_bytes_per_step": (p + 1) * rows * 4,
+            "d2h_bytes_per_step": 2 * rows * 4, "ms_per_step": dt * 1e3, "steps": k,
+            "api": "_polars_plugin_pl_lr_pred_f32 (Arrow C data, pinned host buffers)"}
+
+
+if __name__ == "__main__":
+    main()

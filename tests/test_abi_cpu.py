@@ -1,0 +1,117 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the headers declare,
+its schema twins answer without a GPU, the kwargs/pickle + Arrow import path reaches the device check and fails
+LOUDLY (no CPU fallback) when there is no GPU, and the Student-t code shared with the report kernel matches scipy."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import polars_ds_extension_b200 as pds
+from polars_ds_extension_b200 import _harness
+from polars_ds_extension_b200._lib import lib, LIB_PATH
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    syms = set()
+    h = (ROOT / "include" / "pdsb.h").read_text()
+    syms |= set(re.findall(r"\b(pdsb_[a-z0-9_]+)\s*\(", h))
+    p = (ROOT / "include" / "polars_plugin_abi.h").read_text()
+    for name in re.findall(r"PDSB_DECLARE_EXPR\((\w+)\)", p):
+        if name == "name":
+            continue
+        syms.add(f"_polars_plugin_{name}")
+        syms.add(f"_polars_plugin_field_{name}")
+    syms |= {"_polars_plugin_get_version", "_polars_plugin_get_last_error_message"}
+    return syms
+
+
+def test_library_exports_every_declared_symbol():
+    assert LIB_PATH.exists(), "build with python -m polars_ds_extension_b200.build"
+    L = lib()
+    missing = [s for s in sorted(_declared_symbols()) if not hasattr(L, s)]
+    assert not missing, missing
+    assert len([s for s in _declared_symbols() if s.startswith("_polars_plugin_pl_")]) == 20
+    L._polars_plugin_get_version.restype = C.c_uint32
+    assert L._polars_plugin_get_version() == 1          # major 0, minor 1
+    assert L.pdsb_version() == 0x000100
+
+
+def test_schema_twins():
+    import pyarrow as pa
+
+    for sym in _harness.PLUGIN_SYMBOLS:
+        f = _harness.field_of(sym)
+        T = pa.float32() if sym.endswith("_f32") else pa.float64()
+        base = sym[:-4] if sym.endswith("_f32") else sym
+        if base in ("pl_lr", "pl_lr_multi"):
+            assert f.name == "coeffs" and f.type == pa.large_list(pa.field("item", T))
+        elif base in ("pl_lr_pred", "pl_lr_multi_pred"):
+            assert [c.name for c in f.type] == ["pred", "resid"] and f.type.field(0).type == T
+        elif base == "pl_lr_w_rcond":
+            assert [c.name for c in f.type] == ["coeffs", "singular_values"]
+        elif base in ("pl_lin_reg_report", "pl_wls_report"):
+            assert f.name == "lin_reg_report"
+            assert [c.name for c in f.type] == ["features", "beta", "std_err", "t", "p>|t|", "0.025", "0.975", "r2", "adj_r2"]
+        else:
+            assert [c.name for c in f.type] == ["coeffs", "pred"]
+
+
+def _has_gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the loud failure on a box without a GPU")
+def test_fails_loudly_without_gpu():
+    df = pds.Frame({"x1": np.arange(10.0), "y": np.arange(10.0) * 2})
+    with pytest.raises(pds.PdsbError, match="no CPU fallback"):
+        df.select(pds.lin_reg("x1", target="y"))
+    with pytest.raises(pds.PdsbError, match="no CPU fallback"):
+        df.select(pds.rolling_lin_reg("x1", target="y", window_size=3))
+
+
+def test_kwargs_validation_happens_before_compute():
+    # a kwargs dict without the required serde fields is rejected by the pickle reader (LRKwargs, linear_regression.rs:27-45)
+    import pyarrow as pa
+
+    with pytest.raises(pds.PdsbError, match="missing field|no CPU fallback"):
+        _harness.call_plugin("pl_lr", [pa.array([1.0, 2.0]), pa.array([1.0, 2.0])], ["y", "x"], {"bias": True})
+    with pytest.raises(pds.PdsbError, match="numeric|no CPU fallback"):
+        _harness.call_plugin("pl_lr", [pa.array(["a", "b"]), pa.array([1.0, 2.0])], ["y", "x"],
+                             {"bias": False, "null_policy": "raise", "solver": "qr", "l1_reg": 0.0, "l2_reg": 0.0, "tol": 0.0})
+
+
+def test_student_t_matches_scipy():
+    from scipy import stats
+
+    L = lib()
+    for df in [1.0, 2.0, 3.5, 10.0, 30.0, 297.0, 1e4, 1e6]:
+        for t in [0.0, 0.1, 1.0, 2.5, 7.0, 40.0]:
+            ref = stats.t.sf(t, df)
+            got = L.pdsb_student_t_sf(t, df)
+            assert abs(got - ref) <= 1e-11 * max(ref, 1e-300) + 1e-300 or abs(got - ref) / ref < 1e-9, (df, t, got, ref)
+        ref = stats.t.ppf(0.975, df)
+        assert abs(L.pdsb_student_t_ppf(0.975, df) - ref) / ref < 1e-10, df
+
+
+def test_python_wrappers_build_reference_kwargs():
+    e = pds.lin_reg("a", "b", target="y", add_bias=True, l2_reg=0.1)
+    assert e.symbol == "pl_lr" and [c.out_name for c in e.args] == ["y", "a", "b"] and e.args[0].cast_to == "f64"
+    assert e.kwargs == {"bias": True, "null_policy": "skip", "l1_reg": 0.0, "l2_reg": 0.1, "solver": "qr", "tol": 1e-5,
+                        "max_iter": 200, "weighted": False, "positive": False, "singular_x_tol": 1e-12}
+    e = pds.rolling_lin_reg("a", "b", target="y", window_size=5, l2_reg=-0.2)
+    assert e.kwargs == {"null_policy": "raise", "n": 5, "bias": False, "lambda": 0.2, "min_size": 2}
+    e = pds.lin_reg_report("a", target="y", weights="w")
+    assert e.symbol == "pl_wls_report" and [c.out_name for c in e.args] == ["w", "y", "y", "a"] and e.args[1].agg == "var"
+    with pytest.raises(ValueError):
+        pds.rolling_lin_reg("a", target="y", window_size=1)
+    with pytest.raises(ValueError):
+        pds.lin_reg("a", target=[])
