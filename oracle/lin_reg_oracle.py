@@ -747,8 +747,14 @@ def pl_rolling_lr(inputs, kw, f32=False):
 # rolling == per-window OLS, recursive == prefix OLS; tests/test_linear_exprs.py:123-166,718-854)
 # --------------------------------------------------------------------------------------
 def window_ols(X, y, lo, hi, lam=0.0, add_bias=False):
+    """OLS / ridge on rows [lo, hi) of a design X that already holds the ones column when add_bias.
+
+    For the online (rolling / recursive) family the reference constructs OnlineLR::new(lambda, false) on that
+    matrix (lr_online_solvers.rs:163-165, 195-197), so lambda is added to EVERY diagonal entry including the bias
+    one — unlike pl_lr, where the bias diagonal is exempt (lr_solvers.rs:200-209).  `add_bias` is therefore
+    deliberately ignored here."""
     Xw = np.asarray(X[lo:hi], dtype=np.float64)
     G = Xw.T @ Xw
-    n1 = Xw.shape[1] - int(add_bias)
+    n1 = Xw.shape[1]
     G[np.arange(n1), np.arange(n1)] += lam
     return np.linalg.solve(G, Xw.T @ np.asarray(y[lo:hi], dtype=np.float64))

@@ -1,7 +1,425 @@
-// K2b — placeholder until the tcgen05 kernel lands (replaced in the next milestone).
+// K2b — the headline kernel: moments  M = [X|Y|1]^T [X|Y|1]  for f32 frames on the 5th-gen tensor cores.
+//
+// Replaces faer's matmul in get_xtx_with_lambda / build_xty (/root/reference/src/linear/lr/lr_solvers.rs:183-211,
+// 262-278) and the column sums of faer_coordinate_descent (:483-484): one pass over the frame instead of three.
+//
+// Shape of the problem: Z~ = [Z | 1] has q~ = p + t + 1 <= 64 columns and n ~ 1e8 rows, i.e. a GEMM with M = N = q~
+// and K = n.  At q~ = 34 the FP32 SIMT pipes cannot keep up with HBM (595 FMA per row vs 132 bytes per row), so the
+// Gram goes to tcgen05.mma kind::tf32 — and because one TF32 product loses 13 mantissa bits it is computed as the
+// classic 3-term split  x = hi + lo  (hi = x with the low 13 mantissa bits cleared, lo = x - hi, exact in fp32):
+//        G = HH + LH + LH^T (+ LL ~ 2^-22, dropped),     HH = hi^T hi,  LH = lo^T hi.
+// Both products come out of ONE instruction stream by stacking [hi ; lo] along the MMA's M = 128 dimension (which is
+// free: an M = 64 and an M = 128 instruction cost the same N/2 cycles):
+//        A  (TMEM, 128 lanes x 8 cols per MMA) : lanes 0..63 = hi of column m, lanes 64..127 = lo of column m
+//        B  (SMEM, N x 8, K-major, 128B swizzle): hi of column n            ->  D[0:64] = HH,  D[64:128] = LH
+// Data flow per CTA (persistent, one CTA per SM, contiguous range of 32-row boxes):
+//   warp 0      TMA producer  : cp.async.bulk.tensor {32 rows x q cols} -> raw ring (128B-swizzled, K-major)
+//   warps 2-5   converters    : raw row m -> registers -> hi / lo -> tcgen05.st into the TMEM A ring; the hi half is
+//                               also written to the B ring (so B == hi bit-exactly, independent of how the tensor core
+//                               would round a raw fp32 operand); the "1" column (or the row mask) is synthesised here
+//   warp 1      MMA issuer    : 4 x tcgen05.mma (K = 8) per box, accumulating in TMEM (fp32)
+//   warps 6-9   epilogue      : every FLUSH_BOXES boxes the accumulator is drained with tcgen05.ld and added to f64
+//                               registers (double-buffered D), so fp32 accumulation error never grows with n
+// A second tiny kernel sums the per-CTA partials in a fixed order (bit-reproducible) and applies the symmetrisation.
+// Roofline: HBM-bound, algorithmic bytes = 4 (p + t) per row (+4 with a mask).
 #include "../common.h"
 #include "kernels.h"
+#include <cuda.h>
+#include <cstdlib>
+
 namespace pdsb {
-bool moments_tcgen05_supported(const float*, int64_t, const float*, int64_t, int64_t, int, int) { return false; }
-int moments_tcgen05_f32(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, double*, cudaStream_t) { return -1; }
+
+namespace {
+
+constexpr int BOX_ROWS = 32;            // K extent of one TMA box = 128 bytes of f32 = one swizzle row
+constexpr int BPS = 2;                  // boxes per pipeline stage
+constexpr int STAGE_ROWS = BOX_ROWS * BPS;
+constexpr int MAX_RAW_STAGES = 8;       // TMA landing ring (stage = BPS boxes); 6 when N = 64 (shared-memory budget)
+constexpr int AB_STAGES = 6;            // TMEM-A / SMEM-B ring (6 x 64 columns + 2 x 64 accumulator columns = 512)
+constexpr int FLUSH_STAGES = 8;         // accumulate 8 stages = 512 rows in fp32 before draining to f64
+constexpr int NUM_THREADS = 320;        // 10 warps: TMA, MMA, 4 converters, 4 epilogue
+constexpr int TMEM_COLS = 512;
+constexpr int D_COLS = 64;              // columns reserved per accumulator buffer
+constexpr int A_COL0 = 2 * D_COLS;      // first column of the A ring
+
+// ---------------------------------------------------------------- PTX helpers ----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, M = 128
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+      "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+      "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+
+// UMMA shared-memory descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (SM100 descriptor v1)
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address   bits [0,14)
+  d |= (uint64_t)0 << 16;                           // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset bits [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                           // layout: SWIZZLE_128B
+  return d;
+}
+
+struct alignas(8) Barriers {
+  uint64_t raw_full[MAX_RAW_STAGES], raw_empty[MAX_RAW_STAGES];
+  uint64_t ab_full[AB_STAGES], ab_empty[AB_STAGES];
+  uint64_t d_full[2], d_empty[2];
+  uint32_t tmem_base;
+};
+
+// NB = N / 16 (N = MMA N dimension = padded number of Z~ columns)
+template <int NB>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ mask, int64_t n, int q /* Z cols */,
+                    int64_t stages_total, double* __restrict__ partials /* [grid][128][N] */) {
+  constexpr int N = NB * 16;
+  constexpr int RAW_STAGES = (NB == 4) ? 6 : MAX_RAW_STAGES;
+  constexpr uint32_t TILE_BYTES = N * 128;                 // one box-tile: N rows x 128 bytes
+  extern __shared__ __align__(1024) unsigned char smem[];
+  // carve: raw ring | B ring | barriers
+  unsigned char* raw = smem;                                              // RAW_STAGES * BPS * TILE_BYTES
+  unsigned char* bt = raw + (size_t)RAW_STAGES * BPS * TILE_BYTES;        // AB_STAGES  * BPS * TILE_BYTES
+  Barriers* bars = reinterpret_cast<Barriers*>(bt + (size_t)AB_STAGES * BPS * TILE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = q + 1;                                    // Z~ columns (with the ones / mask column)
+
+  // this CTA's contiguous range of stages
+  const int64_t per = (stages_total + gridDim.x - 1) / gridDim.x;
+  const int64_t s_begin = (int64_t)blockIdx.x * per;
+  const int64_t s_end = min(stages_total, s_begin + per);
+  const int64_t my_stages = s_end > s_begin ? s_end - s_begin : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(&bars->raw_full[i], 1); mbar_init(&bars->raw_empty[i], 4); }
+    for (int i = 0; i < AB_STAGES; ++i) { mbar_init(&bars->ab_full[i], 4); mbar_init(&bars->ab_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->d_full[i], 1); mbar_init(&bars->d_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // zero the B ring once (rows >= qt stay zero forever; rows < qt are rewritten every stage)
+  for (int i = threadIdx.x; i < AB_STAGES * BPS * (int)TILE_BYTES / 16; i += NUM_THREADS)
+    reinterpret_cast<uint4*>(bt)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      for (int64_t i = 0; i < my_stages; ++i) {
+        const int rs = (int)(i % RAW_STAGES);
+        const uint32_t ph = (uint32_t)((i / RAW_STAGES) & 1);
+        mbar_wait(&bars->raw_empty[rs], ph ^ 1);
+        mbar_arrive_expect_tx(&bars->raw_full[rs], (uint32_t)(BPS * q * 128));
+        const int64_t row0 = (s_begin + i) * STAGE_ROWS;
+#pragma unroll
+        for (int b = 0; b < BPS; ++b)
+          tma_load_2d(raw + ((size_t)rs * BPS + b) * TILE_BYTES, &tmap, &bars->raw_full[rs], (int)(row0 + b * BOX_ROWS), 0);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int64_t i = 0; i < my_stages; ++i) {
+        const int s = (int)(i % AB_STAGES);
+        const uint32_t ph = (uint32_t)((i / AB_STAGES) & 1);
+        const int64_t g = i / FLUSH_STAGES;
+        const int buf = (int)(g & 1);
+        const bool first = (i % FLUSH_STAGES) == 0;
+        if (first) { mbar_wait(&bars->d_empty[buf], (uint32_t)(((g >> 1) & 1) ^ 1)); }
+        mbar_wait(&bars->ab_full[s], ph);
+        tc_fence_after();
+        const uint32_t d_addr = tmem + (uint32_t)(buf * D_COLS);
+#pragma unroll
+        for (int b = 0; b < BPS; ++b) {
+          const uint32_t b_base = smem_u32(bt + ((size_t)s * BPS + b) * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BOX_ROWS / 8; ++k) {
+            const uint32_t a_addr = tmem + (uint32_t)(A_COL0 + s * (BPS * BOX_ROWS) + b * BOX_ROWS + k * 8);
+            const uint64_t bd = make_b_desc(b_base + k * 32);
+            tc_mma_tf32_ts(d_addr, a_addr, bd, idesc, (first && b == 0 && k == 0) ? 0u : 1u);
+          }
+        }
+        tc_commit(&bars->ab_empty[s]);
+        if ((i % FLUSH_STAGES) == FLUSH_STAGES - 1 || i == my_stages - 1) tc_commit(&bars->d_full[buf]);
+      }
+    }
+  } else if (warp < 6) {
+    // =============================== converters (4 warps = 128 TMEM lanes) ===============================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
+    const bool is_lo = quad >= 2;
+    const int m = (quad & 1) * 32 + lane;      // Z~ column handled by this thread
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    for (int64_t i = 0; i < my_stages; ++i) {
+      const int rs = (int)(i % RAW_STAGES);
+      const uint32_t rph = (uint32_t)((i / RAW_STAGES) & 1);
+      const int s = (int)(i % AB_STAGES);
+      const uint32_t sph = (uint32_t)((i / AB_STAGES) & 1);
+      mbar_wait(&bars->raw_full[rs], rph);
+      mbar_wait(&bars->ab_empty[s], sph ^ 1);
+      tc_fence_after();
+      const int64_t row0 = (s_begin + i) * STAGE_ROWS;
+#pragma unroll
+      for (int b = 0; b < BPS; ++b) {
+        uint32_t v[32];
+        if (m < q) {
+          const unsigned char* rowp = raw + ((size_t)rs * BPS + b) * TILE_BYTES + (size_t)m * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 x = *reinterpret_cast<const uint4*>(rowp + ((c ^ (m & 7)) << 4));
+            v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+          }
+        } else if (m == q) {
+          const int64_t r0 = row0 + b * BOX_ROWS;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            float o = 0.0f;
+            if (r0 + k < n) o = mask ? __ldg(mask + r0 + k) : 1.0f;
+            v[k] = __float_as_uint(o);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = 0u;
+        }
+        if (!is_lo) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] &= 0xFFFFE000u;          // hi: 10-bit mantissa, exactly representable in TF32
+          if (m < qt) {
+            unsigned char* brow = bt + ((size_t)s * BPS + b) * TILE_BYTES + (size_t)m * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<uint4*>(brow + ((c ^ (m & 7)) << 4)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float x = __uint_as_float(v[k]);
+            const float hi = __uint_as_float(v[k] & 0xFFFFE000u);
+            v[k] = __float_as_uint(x - hi);                              // lo: exact in fp32
+          }
+        }
+        tmem_st32(tmem + lane_addr + (uint32_t)(A_COL0 + s * (BPS * BOX_ROWS) + b * BOX_ROWS), v);
+      }
+      // all reads of the raw stage are done (values are in registers / already consumed)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->raw_empty[rs]);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      fence_async_smem();          // B-tile stores (generic proxy) -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->ab_full[s]);
+    }
+  } else {
+    // =============================== epilogue (4 warps) ===============================
+    const int quad = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    double acc[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) acc[j] = 0.0;
+    const int64_t groups = (my_stages + FLUSH_STAGES - 1) / FLUSH_STAGES;
+    for (int64_t g = 0; g < groups; ++g) {
+      const int buf = (int)(g & 1);
+      mbar_wait(&bars->d_full[buf], (uint32_t)((g >> 1) & 1));
+      tc_fence_after();
+      uint32_t v[N];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) tmem_ld16(tmem + lane_addr + (uint32_t)(buf * D_COLS + c * 16), v + 16 * c);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->d_empty[buf]);
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc[j] += (double)__uint_as_float(v[j]);
+    }
+    double* out = partials + ((size_t)blockIdx.x * 128 + (size_t)(quad * 32 + lane)) * N;
+#pragma unroll
+    for (int j = 0; j < N; ++j) out[j] = acc[j];
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+  }
+}
+
+// Sum the per-CTA partials in a fixed order, then  G~[a][b] = HH[a][b] + LH[a][b] + LH[b][a]  and permute the Z~
+// columns (targets may precede the features in memory) into the moments order [X | Y | 1].
+__global__ void gram_finalize_kernel(const double* __restrict__ partials, int nparts, int N, int p, int t, int zx, int zy,
+                                     double* __restrict__ M) {
+  const int q1 = p + t + 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= q1 * q1) return;
+  const int i = idx / q1, j = idx % q1;
+  auto zcol = [&](int c) { return c < p ? zx + c : (c < p + t ? zy + (c - p) : p + t); };
+  const int a = zcol(i), b = zcol(j);
+  double hh = 0.0, lh_ab = 0.0, lh_ba = 0.0;
+  for (int k = 0; k < nparts; ++k) {
+    const double* P = partials + (size_t)k * 128 * N;
+    hh += P[(size_t)a * N + b];
+    lh_ab += P[(size_t)(64 + a) * N + b];
+    lh_ba += P[(size_t)(64 + b) * N + a];
+  }
+  // keep the result exactly symmetric: evaluate the same expression for (i,j) and (j,i)
+  double hh_t = 0.0;
+  for (int k = 0; k < nparts; ++k) hh_t += partials[(size_t)k * 128 * N + (size_t)b * N + a];
+  M[idx] = 0.5 * (hh + hh_t) + (lh_ab + lh_ba);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// geometry shared by the support check and the launcher
+struct Geometry { const float* base; int q; int zx, zy; bool ok; };
+
+Geometry analyse(const float* X, int64_t ldx, const float* Y, int64_t ldy, int p, int t) {
+  Geometry g{nullptr, p + t, 0, 0, false};
+  if (p < 1 || t < 1 || p + t + 1 > 64) return g;
+  if (ldx != ldy || (ldx % 4) != 0) return g;
+  if (Y == X + (size_t)p * ldx) { g.base = X; g.zx = 0; g.zy = p; g.ok = true; }          // [X | Y]
+  else if (X == Y + (size_t)t * ldy) { g.base = Y; g.zx = t; g.zy = 0; g.ok = true; }     // [Y | X]
+  if (g.ok && (reinterpret_cast<uintptr_t>(g.base) & 15)) g.ok = false;
+  return g;
+}
+
+template <int NB>
+int launch(const CUtensorMap& tmap, const float* mask, int64_t n, int q, int64_t stages_total, int grid, double* partials,
+           cudaStream_t s) {
+  constexpr int N = NB * 16;
+  constexpr int RAW_STAGES = (NB == 4) ? 6 : MAX_RAW_STAGES;
+  const size_t smem = (size_t)(RAW_STAGES + AB_STAGES) * BPS * N * 128 + sizeof(Barriers) + 256;
+  auto k = gram_tcgen05_kernel<NB>;
+  PDSB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, NUM_THREADS, smem, s>>>(tmap, mask, n, q, stages_total, partials);
+  PDSB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+
+bool moments_tcgen05_supported(const float* X, int64_t ldx, const float* Y, int64_t ldy, int64_t n, int p, int t) {
+  if (getenv("PDSB_DISABLE_TCGEN05")) return false;
+  if (n < 4096) return false;                 // latency-bound sizes stay on the SIMT kernel
+  if (!get_encode_fn()) return false;
+  return analyse(X, ldx, Y, ldy, p, t).ok;
+}
+
+int moments_tcgen05_f32(const float* X, int64_t ldx, const float* Y, int64_t ldy, const float* mask, int64_t n, int p,
+                        int t, double* M, cudaStream_t s) {
+  const Geometry g = analyse(X, ldx, Y, ldy, p, t);
+  if (!g.ok) return -1;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return -1;
+  const int q = g.q, qt = q + 1;
+  const int N = ((qt + 15) / 16) * 16;
+  CUtensorMap tmap;
+  cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)q};
+  cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BOX_ROWS, (cuuint32_t)q};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(g.base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return 1; }
+  const int64_t stages_total = ceil_div(n, STAGE_ROWS);
+  int grid = sm_count();
+  if (stages_total < grid) grid = (int)stages_total;
+  double* partials = nullptr;
+  if (dev_alloc((void**)&partials, (size_t)grid * 128 * N * sizeof(double), s)) return 1;
+  int rc;
+  switch (N / 16) {
+    case 1: rc = launch<1>(tmap, mask, n, q, stages_total, grid, partials, s); break;
+    case 2: rc = launch<2>(tmap, mask, n, q, stages_total, grid, partials, s); break;
+    case 3: rc = launch<3>(tmap, mask, n, q, stages_total, grid, partials, s); break;
+    default: rc = launch<4>(tmap, mask, n, q, stages_total, grid, partials, s); break;
+  }
+  if (!rc) {
+    const int q1 = p + t + 1;
+    gram_finalize_kernel<<<(q1 * q1 + 127) / 128, 128, 0, s>>>(partials, grid, N, p, t, g.zx, g.zy, M);
+    cudaError_t e = cudaGetLastError();
+    count_launch();
+    if (e != cudaSuccess) { set_error("gram finalize launch failed: %s", cudaGetErrorString(e)); rc = 1; }
+  }
+  dev_free(partials, s);
+  return rc;
+}
+
 }  // namespace pdsb

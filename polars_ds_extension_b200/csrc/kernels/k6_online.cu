@@ -128,7 +128,10 @@ __device__ __forceinline__ bool chol_solve_reg(const double* W, int p, T lambda,
 #pragma unroll
     for (int j = i; j < D; ++j) { A[i][j] = (T)W[k]; A[j][i] = A[i][j]; ++k; }
 #pragma unroll
-  for (int i = 0; i < D; ++i) { if (i < p) A[i][i] += lambda; beta[i] = (T)W[NG + i]; }
+  // The reference builds OnlineLR::new(lambda, false) on a matrix that already holds the physical ones column
+  // (lr_online_solvers.rs:163-165, 195-197), so lambda lands on EVERY diagonal entry, the bias one included.
+  for (int i = 0; i < D; ++i) { A[i][i] += lambda; beta[i] = (T)W[NG + i]; }
+  (void)p;
   bool ok = true;
 #pragma unroll
   for (int c = 0; c < D; ++c) {

@@ -1,0 +1,97 @@
+"""Device-layer parity of the moments kernels (K2a SIMT and K2b tcgen05/TMA) against numpy float64 on the same
+seeded inputs, through the C ABI (pdsb_dev_moments_*) with torch-allocated device memory."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(torch, n, p, t, dtype, seed, order="xy", scale=1.0):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    ld = (n + 31) // 32 * 32
+    Z = torch.zeros((p + t, ld), dtype=dtype, device="cuda")
+    Z[:, :n] = torch.randn((p + t, n), generator=g, device="cuda", dtype=dtype) * scale + 0.25
+    if order == "xy":
+        X, Y = Z[:p], Z[p:]
+    else:
+        Y, X = Z[:t], Z[t:]
+    return Z, X, Y, ld
+
+
+def _ref(X, Y, n, w=None, mask=None):
+    Zh = np.concatenate([X[:, :n].double().cpu().numpy(), Y[:, :n].double().cpu().numpy(), np.ones((1, n))], axis=0)
+    if mask is not None:
+        Zh[-1] = mask[:n].double().cpu().numpy()
+    W = np.ones(n) if w is None else w[:n].double().cpu().numpy()
+    return (Zh * W) @ Zh.T
+
+
+@pytest.mark.parametrize("n,p,t,order", [(4096, 4, 1, "xy"), (100_003, 32, 1, "yx"), (1_000_000, 32, 1, "xy"),
+                                         (50_000, 8, 3, "yx"), (65_536 * 3 + 17, 62, 1, "xy"), (200_000, 1, 1, "xy"),
+                                         (300_000, 14, 1, "xy"), (300_000, 15, 1, "xy"), (77_777, 47, 1, "yx")])
+def test_tcgen05_moments_vs_numpy(n, p, t, order):
+    import torch
+
+    from polars_ds_extension_b200 import device as dev
+    from polars_ds_extension_b200._lib import lib
+
+    Z, X, Y, ld = _mk(torch, n, p, t, torch.float32, 7 + p, order)
+    ref = _ref(X, Y, n)
+    lib().pdsb_set_moments_path(2)          # force tcgen05 (errors if the shape were unsupported)
+    try:
+        M = dev.moments(X, Y, n=n).cpu().numpy()
+        assert lib().pdsb_last_moments_path() == 1
+    finally:
+        lib().pdsb_set_moments_path(0)
+    lib().pdsb_set_moments_path(1)
+    try:
+        Ms = dev.moments(X, Y, n=n).cpu().numpy()
+    finally:
+        lib().pdsb_set_moments_path(0)
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    err_tc = np.max(np.abs(M - ref) / scale)
+    err_simt = np.max(np.abs(Ms - ref) / scale)
+    # 3xTF32 with f64 flushes: the dropped lo*lo term is ~2^-22; fp32 accumulation over 512 rows ~1e-6
+    assert err_tc < 3e-6, (err_tc, err_simt)
+    assert err_simt < 3e-6, err_simt
+    assert np.array_equal(M, M.T)
+
+
+def test_tcgen05_moments_with_mask_and_repro():
+    import torch
+
+    from polars_ds_extension_b200 import device as dev
+    from polars_ds_extension_b200._lib import lib
+
+    n, p = 500_000, 16
+    Z, X, Y, ld = _mk(torch, n, p, 1, torch.float32, 3)
+    mask = (torch.rand(ld, device="cuda") > 0.2).float()
+    Z[:, :] *= mask[None, :]                      # masked rows are zero in X and Y (packer contract)
+    ref = _ref(X, Y, n, mask=mask)
+    lib().pdsb_set_moments_path(2)
+    try:
+        M1 = dev.moments(X, Y, n=n, mask=mask).cpu().numpy()
+        M2 = dev.moments(X, Y, n=n, mask=mask).cpu().numpy()
+    finally:
+        lib().pdsb_set_moments_path(0)
+    assert np.array_equal(M1, M2)                 # bit-reproducible
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    assert np.max(np.abs(M1 - ref) / scale) < 3e-6
+    assert abs(M1[-1, -1] - float(mask[:n].sum().item())) < 0.5
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_simt_moments_weighted(dtype):
+    import torch
+
+    from polars_ds_extension_b200 import device as dev
+
+    td = torch.float32 if dtype == "f32" else torch.float64
+    n, p, t = 33_333, 5, 2
+    Z, X, Y, ld = _mk(torch, n, p, t, td, 11)
+    w = torch.rand(ld, device="cuda", dtype=td) + 0.5
+    ref = _ref(X, Y, n, w=w)
+    M = dev.moments(X, Y, n=n, w=w).cpu().numpy()
+    tol = 3e-6 if dtype == "f32" else 1e-12
+    assert np.max(np.abs(M - ref) / np.sqrt(np.outer(np.diag(ref), np.diag(ref)))) < tol
