@@ -105,8 +105,9 @@ def synth_on_device(torch, rows, p, seed, device):
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     ld = (rows + 31) // 32 * 32
-    X = torch.empty((p, ld), dtype=torch.float32, device=device)
-    y = torch.zeros((1, ld), dtype=torch.float32, device=device)
+    # one column-major frame [X | y] (the layout the plugin's packer builds; lets the TMA box cover all q columns)
+    Z = torch.zeros((p + 1, ld), dtype=torch.float32, device=device)
+    X, y = Z[:p], Z[p:]
     beta = ((torch.arange(p, device=device) % 7).float() - 3.0) / 4.0
     chunk = 1 << 24
     for c in range(p):

@@ -32,15 +32,19 @@ namespace pdsb {
 namespace {
 
 constexpr int BOX_ROWS = 32;            // K extent of one TMA box = 128 bytes of f32 = one swizzle row
-constexpr int BPS = 2;                  // boxes per pipeline stage
+constexpr int BPS = 4;                  // boxes per pipeline stage  (stage = 128 rows)
 constexpr int STAGE_ROWS = BOX_ROWS * BPS;
-constexpr int MAX_RAW_STAGES = 8;       // TMA landing ring (stage = BPS boxes); 6 when N = 64 (shared-memory budget)
-constexpr int AB_STAGES = 6;            // TMEM-A / SMEM-B ring (6 x 64 columns + 2 x 64 accumulator columns = 512)
-constexpr int FLUSH_STAGES = 8;         // accumulate 8 stages = 512 rows in fp32 before draining to f64
-constexpr int NUM_THREADS = 320;        // 10 warps: TMA, MMA, 4 converters, 4 epilogue
+constexpr int MAX_RAW_STAGES = 4;       // TMA landing ring (3 when N = 64: shared-memory budget)
+constexpr int AB_STAGES = 3;            // TMEM-A / SMEM-B ring (3 x 128 columns + 2 x 64 accumulator columns = 512)
+constexpr int FLUSH_STAGES = 4;         // accumulate 4 stages = 512 rows in fp32 before draining to f64
+constexpr int CONV_SETS = 2;            // converter warp sets (4 warps each), alternating stages
+constexpr int EPI_SETS = 2;             // epilogue warp sets, each draining half of the accumulator columns
+constexpr int NUM_WARPS = 2 + 4 * CONV_SETS + 4 * EPI_SETS;   // TMA, MMA, converters, epilogue
+constexpr int NUM_THREADS = NUM_WARPS * 32;                   // 576
 constexpr int TMEM_COLS = 512;
 constexpr int D_COLS = 64;              // columns reserved per accumulator buffer
 constexpr int A_COL0 = 2 * D_COLS;      // first column of the A ring
+constexpr int A_SLOT_COLS = BPS * BOX_ROWS;
 
 // ---------------------------------------------------------------- PTX helpers ----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,13 +126,31 @@ struct alignas(8) Barriers {
   uint32_t tmem_base;
 };
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+      : "r"(taddr) : "memory");
+}
+
 // NB = N / 16 (N = MMA N dimension = padded number of Z~ columns)
 template <int NB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ mask, int64_t n, int q /* Z cols */,
                     int64_t stages_total, double* __restrict__ partials /* [grid][128][N] */) {
   constexpr int N = NB * 16;
-  constexpr int RAW_STAGES = (NB == 4) ? 6 : MAX_RAW_STAGES;
+  constexpr int NH = N / EPI_SETS;                         // accumulator columns per epilogue set
+  constexpr int RAW_STAGES = (NB == 4) ? 3 : MAX_RAW_STAGES;
   constexpr uint32_t TILE_BYTES = N * 128;                 // one box-tile: N rows x 128 bytes
   extern __shared__ __align__(1024) unsigned char smem[];
   // carve: raw ring | B ring | barriers
@@ -143,12 +165,12 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
   const int64_t per = (stages_total + gridDim.x - 1) / gridDim.x;
   const int64_t s_begin = (int64_t)blockIdx.x * per;
   const int64_t s_end = min(stages_total, s_begin + per);
-  const int64_t my_stages = s_end > s_begin ? s_end - s_begin : 0;
+  const uint32_t my_stages = s_end > s_begin ? (uint32_t)(s_end - s_begin) : 0u;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(&bars->raw_full[i], 1); mbar_init(&bars->raw_empty[i], 4); }
     for (int i = 0; i < AB_STAGES; ++i) { mbar_init(&bars->ab_full[i], 4); mbar_init(&bars->ab_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->d_full[i], 1); mbar_init(&bars->d_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->d_full[i], 1); mbar_init(&bars->d_empty[i], 4 * EPI_SETS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // zero the B ring once (rows >= qt stay zero forever; rows < qt are rewritten every stage)
@@ -165,93 +187,103 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
   const uint32_t tmem = bars->tmem_base;
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
-      for (int64_t i = 0; i < my_stages; ++i) {
-        const int rs = (int)(i % RAW_STAGES);
-        const uint32_t ph = (uint32_t)((i / RAW_STAGES) & 1);
-        mbar_wait(&bars->raw_empty[rs], ph ^ 1);
+    // =============================== TMA producer (warp-uniform loop, one elected lane issues) ===============
+    uint32_t rs = 0, ph = 0;
+    for (uint32_t it = 0; it < my_stages; ++it) {
+      mbar_wait(&bars->raw_empty[rs], ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bars->raw_full[rs], (uint32_t)(BPS * q * 128));
-        const int64_t row0 = (s_begin + i) * STAGE_ROWS;
+        const int64_t row0 = (s_begin + it) * STAGE_ROWS;
 #pragma unroll
         for (int b = 0; b < BPS; ++b)
           tma_load_2d(raw + ((size_t)rs * BPS + b) * TILE_BYTES, &tmap, &bars->raw_full[rs], (int)(row0 + b * BOX_ROWS), 0);
       }
+      __syncwarp();
+      if (++rs == RAW_STAGES) { rs = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      for (int64_t i = 0; i < my_stages; ++i) {
-        const int s = (int)(i % AB_STAGES);
-        const uint32_t ph = (uint32_t)((i / AB_STAGES) & 1);
-        const int64_t g = i / FLUSH_STAGES;
-        const int buf = (int)(g & 1);
-        const bool first = (i % FLUSH_STAGES) == 0;
-        if (first) { mbar_wait(&bars->d_empty[buf], (uint32_t)(((g >> 1) & 1) ^ 1)); }
-        mbar_wait(&bars->ab_full[s], ph);
-        tc_fence_after();
-        const uint32_t d_addr = tmem + (uint32_t)(buf * D_COLS);
+    // =============================== MMA issuer (warp-uniform loop, one elected lane issues) ===============
+    // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t bt_addr = smem_u32(bt);
+    uint32_t s = 0, ph = 0, fl = 0, buf = 0, dph = 0;       // ring slot / phase, position in flush group, D buffer / phase
+    for (uint32_t it = 0; it < my_stages; ++it) {
+      if (fl == 0) mbar_wait(&bars->d_empty[buf], dph ^ 1);
+      mbar_wait(&bars->ab_full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_addr = tmem + buf * D_COLS;
+        const uint32_t a_base = tmem + A_COL0 + s * A_SLOT_COLS;
+        const uint64_t bd0 = make_b_desc(bt_addr + s * (BPS * TILE_BYTES));
 #pragma unroll
         for (int b = 0; b < BPS; ++b) {
-          const uint32_t b_base = smem_u32(bt + ((size_t)s * BPS + b) * TILE_BYTES);
 #pragma unroll
           for (int k = 0; k < BOX_ROWS / 8; ++k) {
-            const uint32_t a_addr = tmem + (uint32_t)(A_COL0 + s * (BPS * BOX_ROWS) + b * BOX_ROWS + k * 8);
-            const uint64_t bd = make_b_desc(b_base + k * 32);
-            tc_mma_tf32_ts(d_addr, a_addr, bd, idesc, (first && b == 0 && k == 0) ? 0u : 1u);
+            // descriptor start address advances in 16-byte units: +TILE_BYTES per box, +32 bytes per K=8 step
+            const uint64_t bd = bd0 + (uint64_t)((b * TILE_BYTES + k * 32) >> 4);
+            tc_mma_tf32_ts(d_addr, a_base + b * BOX_ROWS + k * 8, bd, idesc, (fl == 0 && b == 0 && k == 0) ? 0u : 1u);
           }
         }
         tc_commit(&bars->ab_empty[s]);
-        if ((i % FLUSH_STAGES) == FLUSH_STAGES - 1 || i == my_stages - 1) tc_commit(&bars->d_full[buf]);
+        if (fl == FLUSH_STAGES - 1 || it == my_stages - 1) tc_commit(&bars->d_full[buf]);
       }
+      __syncwarp();
+      if (++s == AB_STAGES) { s = 0; ph ^= 1; }
+      if (++fl == FLUSH_STAGES) { fl = 0; if (buf) dph ^= 1; buf ^= 1; }
     }
-  } else if (warp < 6) {
-    // =============================== converters (4 warps = 128 TMEM lanes) ===============================
+  } else if (warp < 2 + 4 * CONV_SETS) {
+    // =============================== converters: CONV_SETS x 4 warps; set j owns stages it = j (mod CONV_SETS) ===
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
+    const uint32_t set = (uint32_t)(warp - 2) >> 2;
     const bool is_lo = quad >= 2;
     const int m = (quad & 1) * 32 + lane;      // Z~ column handled by this thread
+    const int mrow = m < q ? m : q - 1;        // clamped row for the (always executed) shared-memory loads
+    const bool is_data = m < q, is_ones = (m == q);
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    for (int64_t i = 0; i < my_stages; ++i) {
-      const int rs = (int)(i % RAW_STAGES);
-      const uint32_t rph = (uint32_t)((i / RAW_STAGES) & 1);
-      const int s = (int)(i % AB_STAGES);
-      const uint32_t sph = (uint32_t)((i / AB_STAGES) & 1);
+    const uint32_t sw = (uint32_t)(mrow & 7);
+    for (uint32_t it = set; it < my_stages; it += CONV_SETS) {
+      const uint32_t rs = it % RAW_STAGES, rph = (it / RAW_STAGES) & 1;
+      const uint32_t s = it % AB_STAGES, sph = (it / AB_STAGES) & 1;
       mbar_wait(&bars->raw_full[rs], rph);
       mbar_wait(&bars->ab_empty[s], sph ^ 1);
       tc_fence_after();
-      const int64_t row0 = (s_begin + i) * STAGE_ROWS;
+      const int64_t row0 = (s_begin + it) * STAGE_ROWS;
+      const int64_t left64 = n - row0;
+      const int left = left64 > STAGE_ROWS ? STAGE_ROWS : (int)left64;     // valid rows in this stage (>= 1)
 #pragma unroll
       for (int b = 0; b < BPS; ++b) {
         uint32_t v[32];
-        if (m < q) {
-          const unsigned char* rowp = raw + ((size_t)rs * BPS + b) * TILE_BYTES + (size_t)m * 128;
+        const unsigned char* rowp = raw + ((size_t)rs * BPS + b) * TILE_BYTES + (size_t)mrow * 128;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 x = *reinterpret_cast<const uint4*>(rowp + ((c ^ (m & 7)) << 4));
-            v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
-          }
-        } else if (m == q) {
-          const int64_t r0 = row0 + b * BOX_ROWS;
+        for (int c = 0; c < 8; ++c) {
+          const uint4 x = *reinterpret_cast<const uint4*>(rowp + ((c ^ sw) << 4));
+          v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+        }
+        const int nvalid = left - b * BOX_ROWS;                             // rows of this box that exist (may be <= 0)
+        if (mask != nullptr) {   // warp-uniform branch: coalesced mask load, broadcast to the ones thread by shuffles
+          float mk = 0.0f;
+          if (lane < nvalid) mk = __ldg(mask + row0 + b * BOX_ROWS + lane);
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            float o = 0.0f;
-            if (r0 + k < n) o = mask ? __ldg(mask + r0 + k) : 1.0f;
-            v[k] = __float_as_uint(o);
+            const uint32_t o = __float_as_uint(__shfl_sync(0xffffffffu, mk, k));
+            v[k] = is_data ? v[k] : (is_ones ? o : 0u);
           }
         } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) v[k] = 0u;
+          for (int k = 0; k < 32; ++k) {
+            const uint32_t o = (k < nvalid) ? 0x3F800000u : 0u;
+            v[k] = is_data ? v[k] : (is_ones ? o : 0u);
+          }
         }
         if (!is_lo) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) v[k] &= 0xFFFFE000u;          // hi: 10-bit mantissa, exactly representable in TF32
           if (m < qt) {
             unsigned char* brow = bt + ((size_t)s * BPS + b) * TILE_BYTES + (size_t)m * 128;
+            const uint32_t swb = (uint32_t)(m & 7);
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<uint4*>(brow + ((c ^ (m & 7)) << 4)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+              *reinterpret_cast<uint4*>(brow + ((c ^ swb) << 4)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           }
         } else {
 #pragma unroll
@@ -261,7 +293,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
             v[k] = __float_as_uint(x - hi);                              // lo: exact in fp32
           }
         }
-        tmem_st32(tmem + lane_addr + (uint32_t)(A_COL0 + s * (BPS * BOX_ROWS) + b * BOX_ROWS), v);
+        tmem_st32(tmem + lane_addr + (uint32_t)(A_COL0 + s * A_SLOT_COLS + b * BOX_ROWS), v);
       }
       // all reads of the raw stage are done (values are in registers / already consumed)
       __syncwarp();
@@ -273,30 +305,33 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
       if (lane == 0) mbar_arrive(&bars->ab_full[s]);
     }
   } else {
-    // =============================== epilogue (4 warps) ===============================
+    // =============================== epilogue: EPI_SETS x 4 warps, set e drains columns [e*NH, (e+1)*NH) =========
     const int quad = warp & 3;
+    const int eset = (warp - (2 + 4 * CONV_SETS)) >> 2;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    double acc[N];
+    double acc[NH];
 #pragma unroll
-    for (int j = 0; j < N; ++j) acc[j] = 0.0;
-    const int64_t groups = (my_stages + FLUSH_STAGES - 1) / FLUSH_STAGES;
-    for (int64_t g = 0; g < groups; ++g) {
-      const int buf = (int)(g & 1);
-      mbar_wait(&bars->d_full[buf], (uint32_t)((g >> 1) & 1));
+    for (int j = 0; j < NH; ++j) acc[j] = 0.0;
+    const uint32_t groups = (my_stages + FLUSH_STAGES - 1) / FLUSH_STAGES;
+    uint32_t buf = 0, dph = 0;
+    for (uint32_t g = 0; g < groups; ++g) {
+      mbar_wait(&bars->d_full[buf], dph);
       tc_fence_after();
-      uint32_t v[N];
+      uint32_t v[NH];
 #pragma unroll
-      for (int c = 0; c < NB; ++c) tmem_ld16(tmem + lane_addr + (uint32_t)(buf * D_COLS + c * 16), v + 16 * c);
+      for (int c = 0; c < NH / 8; ++c) tmem_ld8(tmem + lane_addr + (uint32_t)(buf * D_COLS + eset * NH + c * 8), v + 8 * c);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->d_empty[buf]);
 #pragma unroll
-      for (int j = 0; j < N; ++j) acc[j] += (double)__uint_as_float(v[j]);
+      for (int j = 0; j < NH; ++j) acc[j] += (double)__uint_as_float(v[j]);
+      if (buf) dph ^= 1;
+      buf ^= 1;
     }
-    double* out = partials + ((size_t)blockIdx.x * 128 + (size_t)(quad * 32 + lane)) * N;
+    double* out = partials + ((size_t)blockIdx.x * 128 + (size_t)(quad * 32 + lane)) * N + eset * NH;
 #pragma unroll
-    for (int j = 0; j < N; ++j) out[j] = acc[j];
+    for (int j = 0; j < NH; ++j) out[j] = acc[j];
   }
 
   tc_fence_before();
@@ -363,7 +398,7 @@ template <int NB>
 int launch(const CUtensorMap& tmap, const float* mask, int64_t n, int q, int64_t stages_total, int grid, double* partials,
            cudaStream_t s) {
   constexpr int N = NB * 16;
-  constexpr int RAW_STAGES = (NB == 4) ? 6 : MAX_RAW_STAGES;
+  constexpr int RAW_STAGES = (NB == 4) ? 3 : MAX_RAW_STAGES;
   const size_t smem = (size_t)(RAW_STAGES + AB_STAGES) * BPS * N * 128 + sizeof(Barriers) + 256;
   auto k = gram_tcgen05_kernel<NB>;
   PDSB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
