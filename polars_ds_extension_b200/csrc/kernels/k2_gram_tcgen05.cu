@@ -176,6 +176,13 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
   // zero the B ring once (rows >= qt stay zero forever; rows < qt are rewritten every stage)
   for (int i = threadIdx.x; i < AB_STAGES * BPS * (int)TILE_BYTES / 16; i += NUM_THREADS)
     reinterpret_cast<uint4*>(bt)[i] = make_uint4(0, 0, 0, 0);
+  // constant rows of the raw tiles: row q = 1.0f, rows q+1 .. N-1 = 0 (position-independent under the swizzle)
+  for (int i = threadIdx.x; i < RAW_STAGES * BPS * (N - q) * 8; i += NUM_THREADS) {
+    const int tile = i / ((N - q) * 8), rem = i % ((N - q) * 8);
+    const int r = q + rem / 8, c = rem % 8;
+    const uint32_t val = (r == q) ? 0x3F800000u : 0u;
+    *reinterpret_cast<uint4*>(raw + (size_t)tile * TILE_BYTES + (size_t)r * 128 + c * 16) = make_uint4(val, val, val, val);
+  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -237,7 +244,9 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
     const uint32_t set = (uint32_t)(warp - 2) >> 2;
     const bool is_lo = quad >= 2;
     const int m = (quad & 1) * 32 + lane;      // Z~ column handled by this thread
-    const int mrow = m < q ? m : q - 1;        // clamped row for the (always executed) shared-memory loads
+    // Rows >= q of every raw tile are never touched by the TMA (its box has q rows): row q is preset to 1.0 (the
+    // "ones" column) and rows > q to 0, so in the common case every thread runs the same select-free code.
+    const int mrow = m < N ? m : N - 1;
     const bool is_data = m < q, is_ones = (m == q);
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t sw = (uint32_t)(mrow & 7);
@@ -250,6 +259,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
       const int64_t row0 = (s_begin + it) * STAGE_ROWS;
       const int64_t left64 = n - row0;
       const int left = left64 > STAGE_ROWS ? STAGE_ROWS : (int)left64;     // valid rows in this stage (>= 1)
+      const bool fast = (mask == nullptr) && (left == STAGE_ROWS);          // warp-uniform
 #pragma unroll
       for (int b = 0; b < BPS; ++b) {
         uint32_t v[32];
@@ -259,20 +269,22 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
           const uint4 x = *reinterpret_cast<const uint4*>(rowp + ((c ^ sw) << 4));
           v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
         }
-        const int nvalid = left - b * BOX_ROWS;                             // rows of this box that exist (may be <= 0)
-        if (mask != nullptr) {   // warp-uniform branch: coalesced mask load, broadcast to the ones thread by shuffles
-          float mk = 0.0f;
-          if (lane < nvalid) mk = __ldg(mask + row0 + b * BOX_ROWS + lane);
+        if (!fast) {
+          const int nvalid = left - b * BOX_ROWS;                           // rows of this box that exist (may be <= 0)
+          if (mask != nullptr) {   // coalesced mask load, broadcast to the ones thread by shuffles
+            float mk = 0.0f;
+            if (lane < nvalid) mk = __ldg(mask + row0 + b * BOX_ROWS + lane);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const uint32_t o = __float_as_uint(__shfl_sync(0xffffffffu, mk, k));
-            v[k] = is_data ? v[k] : (is_ones ? o : 0u);
-          }
-        } else {
+            for (int k = 0; k < 32; ++k) {
+              const uint32_t o = __float_as_uint(__shfl_sync(0xffffffffu, mk, k));
+              v[k] = is_data ? v[k] : (is_ones ? o : 0u);
+            }
+          } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const uint32_t o = (k < nvalid) ? 0x3F800000u : 0u;
-            v[k] = is_data ? v[k] : (is_ones ? o : 0u);
+            for (int k = 0; k < 32; ++k) {
+              const uint32_t o = (k < nvalid) ? 0x3F800000u : 0u;
+              v[k] = is_data ? v[k] : (is_ones ? o : 0u);
+            }
           }
         }
         if (!is_lo) {
