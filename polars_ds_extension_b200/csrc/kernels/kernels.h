@@ -15,6 +15,7 @@ int moments_simt(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, c
 // -1 "shape not supported by this kernel" (caller uses K2a).
 int moments_tcgen05_f32(const float* X, int64_t ldx, const float* Y, int64_t ldy, const float* mask,
                         int64_t n, int p, int t, double* M, cudaStream_t s);
+void set_tc_mode(int m);   // 0 explicit-hi, 1 raw-hi (default)
 bool moments_tcgen05_supported(const float* X, int64_t ldx, const float* Y, int64_t ldy, int64_t n, int p,
                                int t);
 

@@ -50,12 +50,53 @@ def test_tcgen05_moments_vs_numpy(n, p, t, order):
     finally:
         lib().pdsb_set_moments_path(0)
     scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
-    err_tc = np.max(np.abs(M - ref) / scale)
+    # the default (x-only A) kernel does not produce y_i . y_j for i != j (no consumer needs it): NaN there
+    yy_off = np.zeros_like(ref, dtype=bool)
+    yy_off[p:p + t, p:p + t] = ~np.eye(t, dtype=bool)
+    assert not np.isnan(M[~yy_off]).any()
+    err_tc = np.max(np.abs(M - ref)[~yy_off] / scale[~yy_off])
     err_simt = np.max(np.abs(Ms - ref) / scale)
-    # 3xTF32 with f64 flushes: the dropped lo*lo term is ~2^-22; fp32 accumulation over 512 rows ~1e-6
+    # 3xTF32 with f64 flushes: the dropped lo*lo term is ~2^-22; fp32 (round-toward-zero) accumulation over 256 rows
     assert err_tc < 3e-6, (err_tc, err_simt)
     assert err_simt < 3e-6, err_simt
-    assert np.array_equal(M, M.T)
+    assert np.array_equal(M, M.T, equal_nan=True)
+    # the x-only-A variant (does not produce y_i . y_j for i != j: NaN there) must agree with the default kernel
+    lib().pdsb_set_moments_path(2)
+    lib().pdsb_set_tc_variant(3)
+    try:
+        M3 = dev.moments(X, Y, n=n).cpu().numpy()
+    finally:
+        lib().pdsb_set_tc_variant(1)
+        lib().pdsb_set_moments_path(0)
+    assert np.isnan(M3[yy_off]).all()
+    assert np.max(np.abs(M3 - M)[~yy_off] / scale[~yy_off]) < 3e-6
+
+
+@pytest.mark.parametrize("n,p,masked", [(1_000_003, 32, False), (300_000, 20, True), (70_000, 62, False)])
+def test_tcgen05_raw_hi_matches_explicit_hi(n, p, masked):
+    """The default kernel feeds RAW fp32 to the tensor core as the hi operand (it ignores the low 13 mantissa bits);
+    the explicit-hi kernel clears those bits itself.  If the hardware truncates, both are bit-identical."""
+    import torch
+
+    from polars_ds_extension_b200 import device as dev
+    from polars_ds_extension_b200._lib import lib
+
+    Z, X, Y, ld = _mk(torch, n, p, 1, torch.float32, 21, scale=3.0)
+    mask = None
+    if masked:
+        mask = (torch.rand(ld, device="cuda") > 0.3).float()
+        Z[:, :] *= mask[None, :]
+    L = lib()
+    L.pdsb_set_moments_path(2)
+    try:
+        L.pdsb_set_tc_variant(0)
+        M0 = dev.moments(X, Y, n=n, mask=mask).cpu().numpy()
+        L.pdsb_set_tc_variant(1)
+        M1 = dev.moments(X, Y, n=n, mask=mask).cpu().numpy()
+    finally:
+        L.pdsb_set_tc_variant(1)
+        L.pdsb_set_moments_path(0)
+    assert np.array_equal(M0, M1)
 
 
 def test_tcgen05_moments_with_mask_and_repro():
