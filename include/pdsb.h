@@ -79,6 +79,23 @@ int pdsb_dev_moments_f32(const float* X, int64_t ldx, const float* Y, int64_t ld
 int pdsb_dev_moments_f64(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w,
                          const double* mask, int64_t n, int p, int t, double* M, void* stream);
 
+/* Row-blocked frame: the library's native HBM layout for the f32 headline path.  A frame of `ncols` columns and n rows
+ * stores element (row r, column c) at  frame[(r / 128) * ncols * 128 + c * 128 + (r % 128)]  — i.e. every block of
+ * 128 rows x ncols columns is ONE contiguous run, so a 128-row stage of the Gram kernel is a single sequential
+ * 512*ncols-byte read (measured on B200: a column-major frame caps the TMA pipeline at 4.3 TB/s with all arithmetic
+ * removed, the blocked frame reaches 6.5 TB/s).  Rows >= n of the last block must be zero.  pdsb_frame_elems gives the
+ * allocation size in elements; pdsb_dev_frame_from_colmajor_f32 converts a column-major matrix. */
+#define PDSB_FRAME_ROWS 128
+size_t pdsb_frame_elems(int64_t n, int ncols);
+int pdsb_dev_frame_from_colmajor_f32(const float* src, int64_t ld, int64_t n, int ncols, float* frame, void* stream);
+/* pdsb_dev_moments_f32 / pdsb_dev_predict_f32 on a frame: X = columns [xcol, xcol+p), Y = columns [ycol, ycol+t).
+ * The tcgen05 kernel takes frames with ncols == p + t and X, Y adjacent in either order; other shapes use K2a. */
+int pdsb_dev_moments_frame_f32(const float* frame, int64_t n, int ncols, int xcol, int p, int ycol, int t,
+                               const float* mask, double* M, void* stream);
+int pdsb_dev_predict_frame_f32(const float* frame, int64_t n, int ncols, int xcol, int p, int ycol, int t, int add_bias,
+                               const float* mask, const double* beta, const int* status, float* pred, float* resid,
+                               int64_t ldo, uint8_t* valid, double* ssr, void* stream);
+
 typedef struct pdsb_solve_opts {
   int p, t;              /* features (bias excluded), targets                                          */
   int add_bias;          /* LRKwargs.bias (linear_regression.rs:29)                                     */

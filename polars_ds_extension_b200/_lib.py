@@ -59,6 +59,12 @@ def lib() -> C.CDLL:
                                                                 vp, vp]
         getattr(L, f"pdsb_dev_report_{sfx}").argtypes = [vp, i64, vp, vp, vp, i64, ci, ci, ci, dbl, vp, vp]
     L.pdsb_dev_solve.argtypes = [vp, C.POINTER(SolveOpts), vp, vp, vp, vp]
+    L.pdsb_frame_elems.restype = C.c_size_t
+    L.pdsb_frame_elems.argtypes = [i64, ci]
+    L.pdsb_dev_frame_from_colmajor_f32.argtypes = [vp, i64, i64, ci, vp, vp]
+    L.pdsb_dev_moments_frame_f32.argtypes = [vp, i64, ci, ci, ci, ci, ci, vp, vp, vp]
+    L.pdsb_dev_predict_frame_f32.argtypes = [vp, i64, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, i64, vp, vp, vp]
+    L.pdsb_set_tc_variant.argtypes = [ci]
     _lib = L
     return L
 

@@ -43,6 +43,41 @@ int pdsb_dev_moments_f64(const double* X, int64_t ldx, const double* Y, int64_t 
   return moments_simt<double>(X, ldx, Y, ldy, w, mask, n, p, t, M, (cudaStream_t)stream);
 }
 
+// ---- row-blocked frames ("native" layout of the f32 headline path): [block][column][PDSB_FRAME_ROWS] ----
+size_t pdsb_frame_elems(int64_t n, int ncols) { return (size_t)((n + FRAME_ROWS - 1) / FRAME_ROWS) * FRAME_ROWS * (size_t)ncols; }
+
+int pdsb_dev_frame_from_colmajor_f32(const float* src, int64_t ld, int64_t n, int ncols, float* frame, void* stream) {
+  if (require_device()) return 1;
+  return to_frame<float>(src, ld, n, ncols, frame, (cudaStream_t)stream);
+}
+
+int pdsb_dev_moments_frame_f32(const float* frame, int64_t n, int ncols, int xcol, int p, int ycol, int t,
+                               const float* mask, double* M, void* stream) {
+  if (require_device()) return 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (xcol < 0 || ycol < 0 || xcol + p > ncols || ycol + t > ncols) { set_error("moments_frame: columns out of range"); return 1; }
+  t_last_moments_path = 0;
+  if (g_forced_path.load() != 1) {
+    int rc = moments_tcgen05_frame_f32(frame, n, ncols, xcol, p, ycol, t, mask, M, s);
+    if (rc == 0) { t_last_moments_path = 1; return 0; }
+    if (rc > 0) return rc;
+  }
+  if (g_forced_path.load() == 2) { set_error("moments_frame: tcgen05 path forced but shape unsupported"); return 1; }
+  const int64_t bstride = (int64_t)ncols * FRAME_ROWS;
+  return moments_simt<float>(frame + (size_t)xcol * FRAME_ROWS, 0, frame + (size_t)ycol * FRAME_ROWS, 0, nullptr, mask, n, p, t,
+                             M, s, bstride);
+}
+
+int pdsb_dev_predict_frame_f32(const float* frame, int64_t n, int ncols, int xcol, int p, int ycol, int t, int add_bias,
+                               const float* mask, const double* beta, const int* status, float* pred, float* resid,
+                               int64_t ldo, uint8_t* valid, double* ssr, void* stream) {
+  if (require_device()) return 1;
+  if (xcol < 0 || ycol < 0 || xcol + p > ncols || ycol + t > ncols) { set_error("predict_frame: columns out of range"); return 1; }
+  const int64_t bstride = (int64_t)ncols * FRAME_ROWS;
+  return predict_resid<float>(frame + (size_t)xcol * FRAME_ROWS, 0, frame + (size_t)ycol * FRAME_ROWS, 0, nullptr, mask, n, p,
+                              t, add_bias, beta, status, pred, resid, ldo, valid, ssr, (cudaStream_t)stream, bstride);
+}
+
 int pdsb_dev_solve(const double* M, const pdsb_solve_opts* opts, double* beta, int* status, double* aux,
                    void* stream) {
   if (require_device()) return 1;

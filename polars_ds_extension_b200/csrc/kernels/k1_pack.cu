@@ -44,7 +44,8 @@ __device__ __forceinline__ bool bit_at(const uint8_t* bm, int64_t i) { return (b
 
 template <typename T>
 __global__ void pack_kernel(const void* __restrict__ src, int dtype, const uint8_t* __restrict__ validity,
-                            int64_t bit_offset, int64_t len, T* __restrict__ dst, int mode, double fill) {
+                            int64_t bit_offset, int64_t len, T* __restrict__ dst, int mode, double fill,
+                            int64_t bstride, int64_t row0) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
     double v;
     // `src` is uploaded already offset to the chunk's first element for byte-addressable types; BOOL keeps the
@@ -56,7 +57,22 @@ __global__ void pack_kernel(const void* __restrict__ src, int dtype, const uint8
       else if (mode == 1) v = fill;
       else v = 0.0;
     }
-    dst[i] = (T)v;
+    if (bstride) { const int64_t r = row0 + i; dst[(r >> 7) * bstride + (r & 127)] = (T)v; }   // frame column
+    else dst[i] = (T)v;
+  }
+}
+
+template <typename T>
+__global__ void to_frame_kernel(const T* __restrict__ src, int64_t ld, int64_t n, int ncols, T* __restrict__ frame) {
+  // one thread per (row, column); consecutive threads -> consecutive rows: coalesced on both sides
+  const int64_t nb = (n + 127) >> 7;
+  const int64_t total = nb * 128 * ncols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t blk = i / ((int64_t)ncols * 128);
+    const int64_t rem = i - blk * ncols * 128;
+    const int c = (int)(rem >> 7);
+    const int64_t row = (blk << 7) + (rem & 127);
+    frame[i] = row < n ? src[(int64_t)c * ld + row] : T(0);
   }
 }
 
@@ -107,10 +123,18 @@ inline int grid_for(int64_t len) {
 
 template <typename T>
 int pack_chunk(const void* src, int src_dtype, const uint8_t* validity, int64_t bit_offset, int64_t len,
-               T* dst, int mode, double fill, cudaStream_t s) {
+               T* dst, int mode, double fill, cudaStream_t s, int64_t bstride, int64_t row0) {
   if (len <= 0) return 0;
-  pack_kernel<T><<<grid_for(len), 256, 0, s>>>(src, src_dtype, validity, bit_offset, len, dst, mode, fill);
+  pack_kernel<T><<<grid_for(len), 256, 0, s>>>(src, src_dtype, validity, bit_offset, len, dst, mode, fill, bstride, row0);
   PDSB_AFTER_LAUNCH("pack");
+  return 0;
+}
+template <typename T>
+int to_frame(const T* src, int64_t ld, int64_t n, int ncols, T* frame, cudaStream_t s) {
+  if (n <= 0) return 0;
+  const int64_t total = ((n + 127) >> 7) * 128 * ncols;
+  to_frame_kernel<T><<<grid_for(total), 256, 0, s>>>(src, ld, n, ncols, frame);
+  PDSB_AFTER_LAUNCH("to_frame");
   return 0;
 }
 template <typename T>
@@ -142,7 +166,8 @@ int count_mask(const T* rowmask, int64_t len, double* out, cudaStream_t s) {
 }
 
 #define INST(T)                                                                                              \
-  template int pack_chunk<T>(const void*, int, const uint8_t*, int64_t, int64_t, T*, int, double, cudaStream_t); \
+  template int pack_chunk<T>(const void*, int, const uint8_t*, int64_t, int64_t, T*, int, double, cudaStream_t, int64_t, int64_t); \
+  template int to_frame<T>(const T*, int64_t, int64_t, int, T*, cudaStream_t);                                 \
   template int and_validity<T>(const uint8_t*, int64_t, int64_t, T*, cudaStream_t);                          \
   template int fill_value<T>(T*, int64_t, T, cudaStream_t);                                                  \
   template int zero_masked<T>(T*, const T*, int64_t, cudaStream_t);                                          \

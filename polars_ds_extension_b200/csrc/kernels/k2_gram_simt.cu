@@ -22,7 +22,7 @@ template <typename T, int MAXT, bool WEIGHTED>
 __global__ void __launch_bounds__(256)
 gram_simt_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ Y, int64_t ldy,
                  const T* __restrict__ w, const T* __restrict__ mask, int64_t n, int p, int t,
-                 int tile_r, int S, double* __restrict__ partials) {
+                 int tile_r, int S, double* __restrict__ partials, int64_t bstride /* 0: column-major; else frame block stride */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Zs = reinterpret_cast<T*>(smem_raw);            // [tile_r][S]
   T* ws = Zs + (size_t)tile_r * S;                   // [tile_r]
@@ -62,6 +62,12 @@ gram_simt_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ Y, 
       int64_t row = row0 + r;
       T v = T(0);
       if (row < n) {
+        if (bstride) {   // row-blocked frame: [block][column][FRAME_ROWS]
+          const int64_t o = (row >> 7) * bstride + (row & 127);
+          if (c < p) v = X[o + ((int64_t)c << 7)];
+          else if (c < p + t) v = Y[o + ((int64_t)(c - p) << 7)];
+          else v = mask ? mask[row] : T(1);
+        } else
         if (c < p) v = X[(int64_t)c * ldx + row];
         else if (c < p + t) v = Y[(int64_t)(c - p) * ldy + row];
         else v = mask ? mask[row] : T(1);
@@ -136,15 +142,15 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
 template <typename T, int MAXT>
 static int launch_gram(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, const T* mask,
                        int64_t n, int p, int t, int tile_r, int S, int grid, size_t smem, double* partials,
-                       cudaStream_t s) {
+                       int64_t bstride, cudaStream_t s) {
   if (w) {
     auto k = gram_simt_kernel<T, MAXT, true>;
     PDSB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, tile_r, S, partials);
+    k<<<grid, 256, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, tile_r, S, partials, bstride);
   } else {
     auto k = gram_simt_kernel<T, MAXT, false>;
     PDSB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, tile_r, S, partials);
+    k<<<grid, 256, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, tile_r, S, partials, bstride);
   }
   PDSB_LAUNCH_OK();
   count_launch();
@@ -153,7 +159,7 @@ static int launch_gram(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T
 
 template <typename T>
 int moments_simt(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, const T* mask, int64_t n,
-                 int p, int t, double* M, cudaStream_t s) {
+                 int p, int t, double* M, cudaStream_t s, int64_t bstride) {
   const int q1 = p + t + 1;
   if (p < 0 || t < 0 || q1 > 260) { set_error("moments: p+t+1=%d out of range (max 260)", q1); return 1; }
   const int nt = (q1 + 3) / 4, ntp = nt * (nt + 1) / 2;
@@ -170,10 +176,10 @@ int moments_simt(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, c
   if (dev_alloc((void**)&partials, (size_t)grid * q1 * q1 * sizeof(double), s)) return 1;
   int rc;
   switch (maxt) {
-    case 1: rc = launch_gram<T, 1>(X, ldx, Y, ldy, w, mask, n, p, t, tile_r, S, grid, smem, partials, s); break;
-    case 2: rc = launch_gram<T, 2>(X, ldx, Y, ldy, w, mask, n, p, t, tile_r, S, grid, smem, partials, s); break;
-    case 3: case 4: rc = launch_gram<T, 4>(X, ldx, Y, ldy, w, mask, n, p, t, tile_r, S, grid, smem, partials, s); break;
-    default: rc = launch_gram<T, 9>(X, ldx, Y, ldy, w, mask, n, p, t, tile_r, S, grid, smem, partials, s); break;
+    case 1: rc = launch_gram<T, 1>(X, ldx, Y, ldy, w, mask, n, p, t, tile_r, S, grid, smem, partials, bstride, s); break;
+    case 2: rc = launch_gram<T, 2>(X, ldx, Y, ldy, w, mask, n, p, t, tile_r, S, grid, smem, partials, bstride, s); break;
+    case 3: case 4: rc = launch_gram<T, 4>(X, ldx, Y, ldy, w, mask, n, p, t, tile_r, S, grid, smem, partials, bstride, s); break;
+    default: rc = launch_gram<T, 9>(X, ldx, Y, ldy, w, mask, n, p, t, tile_r, S, grid, smem, partials, bstride, s); break;
   }
   if (rc) { dev_free(partials, s); return rc; }
   int len = q1 * q1;
@@ -186,8 +192,8 @@ int moments_simt(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, c
 }
 
 template int moments_simt<float>(const float*, int64_t, const float*, int64_t, const float*, const float*,
-                                 int64_t, int, int, double*, cudaStream_t);
+                                 int64_t, int, int, double*, cudaStream_t, int64_t);
 template int moments_simt<double>(const double*, int64_t, const double*, int64_t, const double*, const double*,
-                                  int64_t, int, int, double*, cudaStream_t);
+                                  int64_t, int, int, double*, cudaStream_t, int64_t);
 
 }  // namespace pdsb

@@ -40,7 +40,7 @@ constexpr int FLUSH_STAGES = 2;         // accumulate 2 stages = 256 rows in fp3
 constexpr int CONV_SETS = 2;            // converter warp sets (4 warps each), alternating stages
 constexpr int EPI_SETS = 2;             // epilogue warp sets, each draining half of the accumulator columns
 constexpr int NUM_WARPS = 2 + 4 * CONV_SETS + 4 * EPI_SETS;   // TMA, MMA, converters, epilogue
-constexpr int PF_DIST = 8;              // stages the producer warp's L2 prefetches run ahead of its TMA loads
+constexpr int PF_DIST = 0;              // L2-prefetch distance of the producer warp (stages); measured: prefetching does not help (1.63 -> 1.80 ms)
 constexpr int NUM_THREADS = NUM_WARPS * 32;                   // 576
 constexpr int TMEM_COLS = 512;
 constexpr int D_COLS = 64;              // columns reserved per accumulator buffer
@@ -916,10 +916,10 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // geometry shared by the support check and the launcher
-struct Geometry { const float* base; int q; int zx, zy; bool ok; };
+struct Geometry { const float* base; int q; int zx, zy; bool ok; bool blocked; };
 
 Geometry analyse(const float* X, int64_t ldx, const float* Y, int64_t ldy, int p, int t) {
-  Geometry g{nullptr, p + t, 0, 0, false};
+  Geometry g{nullptr, p + t, 0, 0, false, false};
   if (p < 1 || t < 1 || p + t + 1 > 64) return g;
   if (ldx != ldy || (ldx % 4) != 0) return g;
   if (Y == X + (size_t)p * ldx) { g.base = X; g.zx = 0; g.zy = p; g.ok = true; }          // [X | Y]
@@ -945,14 +945,13 @@ int tc_mode() {
 
 template <int NB, int LO_MODE>
 int launch_rawhi(const CUtensorMap& tmap, const float* mask, int64_t n, int q, int64_t stages_total, int grid,
-                 double* partials, const float* zbase, int64_t ld, cudaStream_t s) {
+                 double* partials, const float* zbase, int64_t ld, int blocked, cudaStream_t s) {
   constexpr int N = NB * 16;
   constexpr int RING = (NB == 4) ? 5 : V4_RING;
   const size_t smem = (size_t)RING * BPS * N * 128 + sizeof(BarriersV4) + 256;
   auto k = gram_tcgen05_rawhi_kernel<NB, LO_MODE>;
   PDSB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static int pf = [] { const char* e = getenv("PDSB_TC_PF"); return e ? atoi(e) : PF_DIST; }();
-  static int blocked = [] { const char* e = getenv("PDSB_TC_BLOCKED"); return e ? atoi(e) : 0; }();
   k<<<grid, NUM_THREADS, smem, s>>>(tmap, mask, n, q, stages_total, partials, zbase, ld, pf, blocked);
   PDSB_LAUNCH_OK();
   count_launch();
@@ -961,23 +960,23 @@ int launch_rawhi(const CUtensorMap& tmap, const float* mask, int64_t n, int q, i
 
 template <int NB>
 int launch(const CUtensorMap& tmap, const float* mask, int64_t n, int q, int64_t stages_total, int grid, double* partials,
-           const float* zbase, int64_t ld, cudaStream_t s) {
-  if (tc_mode() == 1) {
+           const float* zbase, int64_t ld, int blocked, cudaStream_t s) {
+  if (tc_mode() == 1 || blocked) {
     // PDSB_TC_DBG (timing ablations only, results are garbage): 1 no TMEM store, 2 no lo arithmetic, 4 no smem loads,
     // 8 no MMA, 15 all of them
     static int dbg = [] { const char* e = getenv("PDSB_TC_DBG"); return e ? atoi(e) : 0; }();
     if (NB == 3) {
       switch (dbg) {
-        case 1: return launch_rawhi<NB, 1>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, s);
-        case 2: return launch_rawhi<NB, 2>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, s);
-        case 4: return launch_rawhi<NB, 4>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, s);
-        case 8: return launch_rawhi<NB, 8>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, s);
-        case 7: return launch_rawhi<NB, 7>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, s);
-        case 15: return launch_rawhi<NB, 15>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, s);
+        case 1: return launch_rawhi<NB, 1>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, blocked, s);
+        case 2: return launch_rawhi<NB, 2>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, blocked, s);
+        case 4: return launch_rawhi<NB, 4>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, blocked, s);
+        case 8: return launch_rawhi<NB, 8>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, blocked, s);
+        case 7: return launch_rawhi<NB, 7>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, blocked, s);
+        case 15: return launch_rawhi<NB, 15>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, blocked, s);
         default: break;
       }
     }
-    return launch_rawhi<NB, 0>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, s);
+    return launch_rawhi<NB, 0>(tmap, mask, n, q, stages_total, grid, partials, zbase, ld, blocked, s);
   }
   constexpr int N = NB * 16;
   constexpr int RAW_STAGES = (NB == 4) ? 3 : MAX_RAW_STAGES;
@@ -1021,20 +1020,43 @@ bool moments_tcgen05_supported(const float* X, int64_t ldx, const float* Y, int6
   return analyse(X, ldx, Y, ldy, p, t).ok;
 }
 
+static int moments_tcgen05_core(const Geometry& g, int64_t ldx, const float* mask, int64_t n, int p, int t, double* M,
+                                cudaStream_t s);
+
 int moments_tcgen05_f32(const float* X, int64_t ldx, const float* Y, int64_t ldy, const float* mask, int64_t n, int p,
                         int t, double* M, cudaStream_t s) {
   const Geometry g = analyse(X, ldx, Y, ldy, p, t);
   if (!g.ok) return -1;
+  return moments_tcgen05_core(g, ldx, mask, n, p, t, M, s);
+}
+
+// row-blocked frame: [block][column][FRAME_ROWS]; the frame holds exactly the p + t columns, X at xcol, Y at ycol
+bool moments_tcgen05_frame_supported(int64_t n, int ncols, int xcol, int p, int ycol, int t) {
+  if (getenv("PDSB_DISABLE_TCGEN05") || !get_encode_fn()) return false;
+  if (n < 4096 || p < 1 || t < 1 || p + t + 1 > 64 || ncols != p + t) return false;
+  return (xcol == 0 && ycol == p) || (ycol == 0 && xcol == t);
+}
+
+int moments_tcgen05_frame_f32(const float* frame, int64_t n, int ncols, int xcol, int p, int ycol, int t, const float* mask,
+                              double* M, cudaStream_t s) {
+  if (!moments_tcgen05_frame_supported(n, ncols, xcol, p, ycol, t)) return -1;
+  if (reinterpret_cast<uintptr_t>(frame) & 15) return -1;
+  Geometry g{frame, p + t, xcol, ycol, true, true};
+  return moments_tcgen05_core(g, 0, mask, n, p, t, M, s);
+}
+
+static int moments_tcgen05_core(const Geometry& g, int64_t ldx, const float* mask, int64_t n, int p, int t, double* M,
+                                cudaStream_t s) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return -1;
   const int q = g.q, qt = q + 1;
-  const bool xonly = (tc_mode() == 3) && (p + 2 * t + 1 <= 64) && t <= 4;
+  const bool xonly = (tc_mode() == 3) && !g.blocked && (p + 2 * t + 1 <= 64) && t <= 4;
   const int N = xonly ? ((p + 2 * t + 1 + 15) / 16) * 16 : ((qt + 15) / 16) * 16;
   CUtensorMap tmap;
   CUresult cr;
-  static int blocked_layout = [] { const char* e = getenv("PDSB_TC_BLOCKED"); return e ? atoi(e) : 0; }();
-  if (blocked_layout) {
-    // experiment: the frame is stored row-blocked, [block][column][128 rows] (each 128-row x q block contiguous)
+  if (g.blocked) {
+    // row-blocked frame: [block][column][128 rows] -> every 128-row x q stage is ONE contiguous 512*q-byte run in HBM.
+    // (column-major frames cap this kernel at 4.3 TB/s even with all arithmetic removed; blocked: 6.5 TB/s)
     cuuint64_t dims3[3] = {(cuuint64_t)STAGE_ROWS, (cuuint64_t)q, (cuuint64_t)ceil_div(n, STAGE_ROWS)};
     cuuint64_t strides3[2] = {(cuuint64_t)STAGE_ROWS * sizeof(float), (cuuint64_t)STAGE_ROWS * q * sizeof(float)};
     cuuint32_t box3[3] = {(cuuint32_t)BOX_ROWS, (cuuint32_t)q, 1};
@@ -1082,10 +1104,10 @@ int moments_tcgen05_f32(const float* X, int64_t ldx, const float* Y, int64_t ldy
     return rc;
   }
   switch (N / 16) {
-    case 1: rc = launch<1>(tmap, mask, n, q, stages_total, grid, partials, g.base, ldx, s); break;
-    case 2: rc = launch<2>(tmap, mask, n, q, stages_total, grid, partials, g.base, ldx, s); break;
-    case 3: rc = launch<3>(tmap, mask, n, q, stages_total, grid, partials, g.base, ldx, s); break;
-    default: rc = launch<4>(tmap, mask, n, q, stages_total, grid, partials, g.base, ldx, s); break;
+    case 1: rc = launch<1>(tmap, mask, n, q, stages_total, grid, partials, g.base, ldx, g.blocked ? 1 : 0, s); break;
+    case 2: rc = launch<2>(tmap, mask, n, q, stages_total, grid, partials, g.base, ldx, g.blocked ? 1 : 0, s); break;
+    case 3: rc = launch<3>(tmap, mask, n, q, stages_total, grid, partials, g.base, ldx, g.blocked ? 1 : 0, s); break;
+    default: rc = launch<4>(tmap, mask, n, q, stages_total, grid, partials, g.base, ldx, g.blocked ? 1 : 0, s); break;
   }
   if (!rc) {
     gram_finalize_kernel<<<(q1 * q1 + 127) / 128, 128, 0, s>>>(partials, grid, N, p, t, g.zx, g.zy, M);

@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(256)
 predict_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ Y, int64_t ldy,
                const T* __restrict__ w, const T* __restrict__ mask, int64_t n, int p, int t, int add_bias,
                const double* __restrict__ beta, const int* __restrict__ status, T* __restrict__ pred,
-               T* __restrict__ resid, int64_t ldo, uint8_t* __restrict__ valid, double* __restrict__ ssr_part) {
+               T* __restrict__ resid, int64_t ldo, uint8_t* __restrict__ valid, double* __restrict__ ssr_part,
+               int64_t bstride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sb = reinterpret_cast<T*>(smem_raw);  // [(p+1) x t]
   const int q = p + (add_bias ? 1 : 0);
@@ -52,7 +53,7 @@ predict_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ Y, in
       for (int v = 0; v < VEC; ++v) acc[v] = sb[k0 * (p + 1) + p];
       for (int c = 0; c < p; ++c) {
         const T b = sb[k0 * (p + 1) + c];
-        const T* src = X + (int64_t)c * ldx + row;
+        const T* src = bstride ? X + (row >> 7) * bstride + ((int64_t)c << 7) + (row & 127) : X + (int64_t)c * ldx + row;
         T xv[VEC];
         if (full) { V tmp = *reinterpret_cast<const V*>(src); memcpy(xv, &tmp, sizeof(V)); }
         else {
@@ -63,7 +64,7 @@ predict_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ Y, in
         for (int v = 0; v < VEC; ++v) acc[v] = fma(xv[v], b, acc[v]);
       }
       T yv[VEC], rv[VEC], mv[VEC], wv[VEC];
-      const T* ys = Y + (int64_t)k0 * ldy + row;
+      const T* ys = bstride ? Y + (row >> 7) * bstride + ((int64_t)k0 << 7) + (row & 127) : Y + (int64_t)k0 * ldy + row;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         bool in = row + v < n;
@@ -126,12 +127,12 @@ __global__ void ssr_reduce_kernel(const double* __restrict__ part, int nblocks, 
 template <typename T>
 int predict_resid(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, const T* mask, int64_t n,
                   int p, int t, int add_bias, const double* beta, const int* status, T* pred, T* resid,
-                  int64_t ldo, uint8_t* valid, double* ssr, cudaStream_t s) {
+                  int64_t ldo, uint8_t* valid, double* ssr, cudaStream_t s, int64_t bstride) {
   if (n <= 0) return 0;
   if (ssr && t > 4) { set_error("predict: ssr supports at most 4 targets"); return 1; }
   constexpr int VEC = sizeof(T) == 4 ? 4 : 2;
   auto aligned = [&](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
-  bool vec_ok = aligned(X) && aligned(pred) && aligned(resid) && (ldx % VEC == 0) && (ldo % VEC == 0);
+  bool vec_ok = aligned(X) && aligned(pred) && aligned(resid) && (bstride || ldx % VEC == 0) && (ldo % VEC == 0);
   const int64_t work = vec_ok ? ceil_div(n, VEC) : n;
   int grid = (int)std::min<int64_t>(ceil_div(work, 256), (int64_t)sm_count() * 8);
   if (grid < 1) grid = 1;
@@ -141,11 +142,11 @@ int predict_resid(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, 
   if (vec_ok) {
     auto k = predict_kernel<T, VEC>;
     if (smem > 48 * 1024) PDSB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, add_bias, beta, status, pred, resid, ldo, valid, part);
+    k<<<grid, 256, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, add_bias, beta, status, pred, resid, ldo, valid, part, bstride);
   } else {
     auto k = predict_kernel<T, 1>;
     if (smem > 48 * 1024) PDSB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, add_bias, beta, status, pred, resid, ldo, valid, part);
+    k<<<grid, 256, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, add_bias, beta, status, pred, resid, ldo, valid, part, bstride);
   }
   cudaError_t e = cudaGetLastError();
   count_launch();
@@ -161,9 +162,9 @@ int predict_resid(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, 
 
 template int predict_resid<float>(const float*, int64_t, const float*, int64_t, const float*, const float*,
                                   int64_t, int, int, int, const double*, const int*, float*, float*, int64_t,
-                                  uint8_t*, double*, cudaStream_t);
+                                  uint8_t*, double*, cudaStream_t, int64_t);
 template int predict_resid<double>(const double*, int64_t, const double*, int64_t, const double*, const double*,
                                    int64_t, int, int, int, const double*, const int*, double*, double*, int64_t,
-                                   uint8_t*, double*, cudaStream_t);
+                                   uint8_t*, double*, cudaStream_t, int64_t);
 
 }  // namespace pdsb

@@ -9,13 +9,17 @@ namespace pdsb {
 // K2a generic SIMT moments (f32 / f64, weights, mask)
 template <typename T>
 int moments_simt(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, const T* mask, int64_t n,
-                 int p, int t, double* M, cudaStream_t s);
+                 int p, int t, double* M, cudaStream_t s, int64_t bstride = 0 /* frame block stride (elements) or 0 */);
 
 // K2b tcgen05 + TMA moments, f32, 3xTF32 split (hi/lo), f64 flush.  Returns 0 ok, 1 error,
 // -1 "shape not supported by this kernel" (caller uses K2a).
 int moments_tcgen05_f32(const float* X, int64_t ldx, const float* Y, int64_t ldy, const float* mask,
                         int64_t n, int p, int t, double* M, cudaStream_t s);
-void set_tc_mode(int m);   // 0 explicit-hi, 1 raw-hi (default)
+void set_tc_mode(int m);   // 0 explicit-hi, 1 raw-hi (default), 3 x-only A
+constexpr int FRAME_ROWS = 128;   // rows per block of the row-blocked frame layout: [block][column][FRAME_ROWS]
+bool moments_tcgen05_frame_supported(int64_t n, int ncols, int xcol, int p, int ycol, int t);
+int moments_tcgen05_frame_f32(const float* frame, int64_t n, int ncols, int xcol, int p, int ycol, int t, const float* mask,
+                              double* M, cudaStream_t s);
 bool moments_tcgen05_supported(const float* X, int64_t ldx, const float* Y, int64_t ldy, int64_t n, int p,
                                int t);
 
@@ -27,13 +31,16 @@ int solve_from_moments(const double* M, const pdsb_solve_opts& o, double* beta, 
 template <typename T>
 int predict_resid(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, const T* mask, int64_t n,
                   int p, int t, int add_bias, const double* beta, const int* status, T* pred, T* resid,
-                  int64_t ldo, uint8_t* valid, double* ssr, cudaStream_t s);
+                  int64_t ldo, uint8_t* valid, double* ssr, cudaStream_t s, int64_t bstride = 0);
 
 // K1 pack: src column chunk (any numeric dtype, optional validity bitmap) -> T column
 // mode: 0 null->NaN, 1 null->fill, 2 null->0 (row masked elsewhere)
 template <typename T>
 int pack_chunk(const void* src, int src_dtype, const uint8_t* validity, int64_t bit_offset, int64_t len,
-               T* dst, int mode, double fill, cudaStream_t s);
+               T* dst, int mode, double fill, cudaStream_t s, int64_t bstride = 0, int64_t row0 = 0);
+// column-major [n x ncols] (ld) -> row-blocked frame
+template <typename T>
+int to_frame(const T* src, int64_t ld, int64_t n, int ncols, T* frame, cudaStream_t s);
 // rowmask[i] &= validity bit (rowmask pre-set to 1)
 template <typename T>
 int and_validity(const uint8_t* validity, int64_t bit_offset, int64_t len, T* rowmask, cudaStream_t s);

@@ -109,5 +109,39 @@ def online_lin_reg(X: torch.Tensor, y: torch.Tensor, window: int, min_rows: int,
     return coeffs, pred, valid
 
 
+FRAME_ROWS = 128
+
+
+def frame_elems(n: int, ncols: int) -> int:
+    return int(lib().pdsb_frame_elems(n, ncols))
+
+
+def to_frame(Z: torch.Tensor, n: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Column-major (ncols, ld) float32 matrix -> row-blocked frame [block][column][128] (flat tensor)."""
+    ncols = Z.shape[0]
+    n = Z.shape[1] if n is None else n
+    frame = out if out is not None else torch.empty(frame_elems(n, ncols), dtype=torch.float32, device=Z.device)
+    check(lib().pdsb_dev_frame_from_colmajor_f32(_ptr(Z), _ld(Z), n, ncols, _ptr(frame), _stream()))
+    return frame
+
+
+def moments_frame(frame: torch.Tensor, n: int, ncols: int, xcol: int, p: int, ycol: int, t: int = 1,
+                  mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    q1 = p + t + 1
+    M = out if out is not None else torch.empty((q1, q1), dtype=torch.float64, device=frame.device)
+    check(lib().pdsb_dev_moments_frame_f32(_ptr(frame), n, ncols, xcol, p, ycol, t, _ptr(mask), _ptr(M), _stream()))
+    return M
+
+
+def predict_frame(frame: torch.Tensor, n: int, ncols: int, xcol: int, p: int, ycol: int, t: int, beta: torch.Tensor,
+                  status: Optional[torch.Tensor], add_bias: bool, pred: torch.Tensor, resid: torch.Tensor,
+                  mask: Optional[torch.Tensor] = None, valid: Optional[torch.Tensor] = None,
+                  ssr: Optional[torch.Tensor] = None):
+    check(lib().pdsb_dev_predict_frame_f32(_ptr(frame), n, ncols, xcol, p, ycol, t, int(add_bias), _ptr(mask), _ptr(beta),
+                                           _ptr(status), _ptr(pred), _ptr(resid), _ld(pred), _ptr(valid), _ptr(ssr),
+                                           _stream()))
+    return pred, resid
+
+
 def launch_count() -> int:
     return int(lib().pdsb_kernel_launch_count())
