@@ -179,6 +179,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
+    from polars_ds_extension_b200._lib import check
+    check(lib().pdsb_set_device(local_rank))
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -189,7 +191,7 @@ def main():
 
     X, y, ld = synth_on_device(torch, rows, p, 208 + rank, device)
     e2e_host = None
-    if rank == 0 and not args.no_e2e:
+    if not args.no_e2e:                                            # every rank pushes its own shard through the plugin
         e2e_host = stage_host_copy(torch, X, y, rows, p)          # column-major host (Arrow) buffers for the e2e leg
     # resident layout of the hot path: the library's row-blocked frame ([block][column][128], include/pdsb.h)
     Zcm = X._base if X._base is not None else torch.cat([X, y])
@@ -267,8 +269,17 @@ def main():
     coef_err = float(np.max(np.abs(beta.cpu().numpy()[0] - bt)))
 
     e2e = None
-    if rank == 0 and not args.no_e2e:
-        e2e = run_e2e(torch, e2e_host, rows, p, args)
+    if not args.no_e2e:
+        barrier()
+        e2e = run_e2e(torch, e2e_host, rows, p, args, barrier)
+        if world > 1 and e2e.get("value"):
+            t_e = torch.tensor([e2e["ms_per_step"]], dtype=torch.float64, device=device)
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+            e2e["ms_per_step"] = float(t_e.item())
+            e2e["value"] = rows * n_gpus / (e2e["ms_per_step"] * 1e-3)
+            e2e["h2d_bytes_per_step"] *= n_gpus
+            e2e["d2h_bytes_per_step"] *= n_gpus
+            e2e["api"] += f"; {n_gpus} ranks concurrently, max over ranks"
 
     cpu = None
     if rank == 0 and not args.no_cpu and n_gpus == 1:
@@ -315,7 +326,7 @@ def stage_host_copy(torch, X, y, rows, p):
     return host
 
 
-def run_e2e(torch, host, rows, p, args):
+def run_e2e(torch, host, rows, p, args, barrier=None):
     """Through the plugin C ABI with host buffers: what a Polars user of the drop-in library would time."""
     import pyarrow as pa
 
@@ -333,6 +344,8 @@ def run_e2e(torch, host, rows, p, args):
     res = _harness.call_plugin("pl_lr_pred_f32", inputs, names, kw)
     del res
     torch.cuda.synchronize()
+    if barrier is not None:
+        barrier()
     k = max(1, args.e2e_steps)
     t0 = time.perf_counter()
     for _ in range(k):

@@ -61,6 +61,8 @@ int64_t pdsb_kernel_launch_count(void);
 int pdsb_last_moments_path(void);
 /* force a path for the f32 moments: 0 auto, 1 simt, 2 tcgen05 (tests / ncu) */
 void pdsb_set_moments_path(int path);
+/* make `device` current for the calling thread inside the library's (statically linked) CUDA runtime */
+int pdsb_set_device(int device);
 /* tcgen05 kernel variant: 1 raw-hi (default; B operand = raw TMA tile, hardware truncation), 0 explicit-hi cross-check */
 void pdsb_set_tc_variant(int v);
 

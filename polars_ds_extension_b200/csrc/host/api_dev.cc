@@ -17,6 +17,11 @@ int64_t pdsb_kernel_launch_count(void) { return g_kernel_launches.load(); }
 int pdsb_last_moments_path(void) { return t_last_moments_path; }
 void pdsb_set_moments_path(int path) { g_forced_path.store(path); }
 void pdsb_set_tc_variant(int v) { set_tc_mode(v); }
+int pdsb_set_device(int device) {
+  if (require_device()) return 1;
+  PDSB_CUDA_OK(cudaSetDevice(device));
+  return 0;
+}
 
 // host-callable special functions (unit-tested against scipy on the CPU; the same code runs in K9)
 double pdsb_student_t_sf(double x, double df) { return student_t_sf(x, df); }

@@ -20,17 +20,20 @@ sc = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
 err = np.nan_to_num(np.abs(M - ref) / sc)
 big = 50_000_000 // 128 * 128
 Zb = torch.randn((p + 1, big), device="cuda")
-if os.environ.get("PDSB_TC_BLOCKED"):
-    # [block][column][128]: same bytes, each 128-row x q block contiguous; the kernel is told via the env var
-    Zb = Zb.view(p + 1, big // 128, 128).permute(1, 0, 2).contiguous().view(p + 1, big)
 Mb = torch.empty((p + 2, p + 2), dtype=torch.float64, device="cuda")
+use_frame = os.environ.get("PDSB_FRAME", "1") != "0"
+if use_frame:
+    Fb = dev.to_frame(Zb, n=big)
+    run = lambda: dev.moments_frame(Fb, big, p + 1, 0, p, p, 1, out=Mb)
+else:
+    run = lambda: dev.moments(Zb[:p], Zb[p:], n=big, out=Mb)
 for _ in range(3):
-    dev.moments(Zb[:p], Zb[p:], n=big, out=Mb)
+    run()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(10):
-    dev.moments(Zb[:p], Zb[p:], n=big, out=Mb)
+    run()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
-print(f"mode={os.environ.get('PDSB_TC_MODE','0')} max_rel_err={err.max():.3e} diag_err={np.abs(np.diag(M)-np.diag(ref)).max()/np.diag(ref).max():.3e} "
+print(f"variant={os.environ.get('PDSB_TC_MODE','1')} dbg={os.environ.get('PDSB_TC_DBG','0')} frame={int(use_frame)} max_rel_err={err.max():.3e} "
       f"ms(5e7 rows)={ms:.3f} GB/s={big*(p+1)*4/ms/1e6:.0f}")
