@@ -880,23 +880,35 @@ __global__ void gram_finalize_xonly_kernel(const double* __restrict__ partials, 
 // columns (targets may precede the features in memory) into the moments order [X | Y | 1].
 __global__ void gram_finalize_kernel(const double* __restrict__ partials, int nparts, int N, int p, int t, int zx, int zy,
                                      double* __restrict__ M) {
+  // one warp per output element of the upper triangle: lane l sums parts l, l+32, ... then a fixed-order xor tree
+  // (bit-reproducible); the mirrored element gets the same value -> exactly symmetric
   const int q1 = p + t + 1;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (idx >= q1 * q1) return;
   const int i = idx / q1, j = idx % q1;
+  if (i > j) return;
   auto zcol = [&](int c) { return c < p ? zx + c : (c < p + t ? zy + (c - p) : p + t); };
   const int a = zcol(i), b = zcol(j);
-  double hh = 0.0, lh_ab = 0.0, lh_ba = 0.0;
-  for (int k = 0; k < nparts; ++k) {
+  double hh = 0.0, hh_t = 0.0, lh_ab = 0.0, lh_ba = 0.0;
+  for (int k = lane; k < nparts; k += 32) {
     const double* P = partials + (size_t)k * 128 * N;
     hh += P[(size_t)a * N + b];
+    hh_t += P[(size_t)b * N + a];
     lh_ab += P[(size_t)(64 + a) * N + b];
     lh_ba += P[(size_t)(64 + b) * N + a];
   }
-  // keep the result exactly symmetric: evaluate the same expression for (i,j) and (j,i)
-  double hh_t = 0.0;
-  for (int k = 0; k < nparts; ++k) hh_t += partials[(size_t)k * 128 * N + (size_t)b * N + a];
-  M[idx] = 0.5 * (hh + hh_t) + (lh_ab + lh_ba);
+  for (int off = 16; off; off >>= 1) {
+    hh += __shfl_xor_sync(0xffffffffu, hh, off);
+    hh_t += __shfl_xor_sync(0xffffffffu, hh_t, off);
+    lh_ab += __shfl_xor_sync(0xffffffffu, lh_ab, off);
+    lh_ba += __shfl_xor_sync(0xffffffffu, lh_ba, off);
+  }
+  if (lane == 0) {
+    const double r = 0.5 * (hh + hh_t) + (lh_ab + lh_ba);
+    M[(size_t)i * q1 + j] = r;
+    M[(size_t)j * q1 + i] = r;
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1110,7 +1122,7 @@ static int moments_tcgen05_core(const Geometry& g, int64_t ldx, const float* mas
     default: rc = launch<4>(tmap, mask, n, q, stages_total, grid, partials, g.base, ldx, g.blocked ? 1 : 0, s); break;
   }
   if (!rc) {
-    gram_finalize_kernel<<<(q1 * q1 + 127) / 128, 128, 0, s>>>(partials, grid, N, p, t, g.zx, g.zy, M);
+    gram_finalize_kernel<<<(q1 * q1 + 7) / 8, 256, 0, s>>>(partials, grid, N, p, t, g.zx, g.zy, M);   // 8 warps = 8 elements per block
     cudaError_t e = cudaGetLastError();
     count_launch();
     if (e != cudaSuccess) { set_error("gram finalize launch failed: %s", cudaGetErrorString(e)); rc = 1; }

@@ -37,7 +37,7 @@ __device__ __forceinline__ double& at(double* A, int q, int i, int j) { return A
 // ---- Householder QR with column pivoting; applies Q^T to B (nb columns) ----
 __device__ void qr_pivot(double* A, int q, double* B, int nb, int* perm, double* cn, double* tau_v0) {
   __shared__ int sh_piv;
-  __shared__ double sh_v0, sh_beta, sh_alpha;
+  __shared__ double sh_v0, sh_beta, sh_alpha, sh_s;
   const int tid = threadIdx.x;
   for (int j = tid; j < q; j += NT) perm[j] = j;
   __syncthreads();
@@ -48,10 +48,15 @@ __device__ void qr_pivot(double* A, int q, double* B, int nb, int* perm, double*
       cn[j] = s;
     }
     __syncthreads();
-    if (tid == 0) {
-      int piv = k; double best = cn[k];
-      for (int j = k + 1; j < q; ++j) if (cn[j] > best) { best = cn[j]; piv = j; }
-      sh_piv = piv;
+    if (tid < 32) {   // warp 0: arg-max of the trailing column norms (ties -> lowest index, like a serial scan)
+      int piv = k; double best = -1.0;
+      for (int j = k + tid; j < q; j += 32) { const double c = cn[j]; if (c > best) { best = c; piv = j; } }
+      for (int off = 16; off; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int op = __shfl_xor_sync(0xffffffffu, piv, off);
+        if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+      }
+      if (tid == 0) { sh_piv = piv; sh_s = best < 0.0 ? 0.0 : best; }
     }
     __syncthreads();
     const int piv = sh_piv;
@@ -61,8 +66,7 @@ __device__ void qr_pivot(double* A, int q, double* B, int nb, int* perm, double*
     }
     __syncthreads();
     if (tid == 0) {
-      double s = 0.0;
-      for (int i = k; i < q; ++i) { double v = at(A, q, i, k); s += v * v; }
+      const double s = sh_s;                       // = sum_{i>=k} A[i,k]^2 of the pivot column (computed above)
       double normx = sqrt(s);
       double x0 = at(A, q, k, k);
       double alpha = (x0 >= 0.0) ? -normx : normx;
@@ -214,7 +218,7 @@ __device__ void jacobi_eigen(double* A, double* V, int q, double* cs) {
 }
 
 struct SolveParams {
-  const double* M; pdsb_solve_opts o; double* beta; int* status; double* aux; Ws ws;
+  const double* M; pdsb_solve_opts o; double* beta; int* status; double* aux; Ws ws; int use_smem;
 };
 
 __device__ __forceinline__ int fidx(int i, int p, int t) { return i < p ? i : p + t; }  // feature i -> moments index
@@ -224,7 +228,9 @@ __global__ void __launch_bounds__(NT) solve_kernel(SolveParams P) {
   const int p = o.p, t = o.t, q1 = p + t + 1;
   const int q = p + (o.add_bias ? 1 : 0);
   const double* M = P.M;
+  extern __shared__ double solve_smem[];
   double* A = P.ws.A; double* V = P.ws.V; double* B = P.ws.B; double* G = P.ws.G;
+  if (P.use_smem) { A = solve_smem; B = solve_smem + (size_t)(p + (o.add_bias ? 1 : 0)) * (p + (o.add_bias ? 1 : 0)); }   // hot matrices on chip
   double* vec = P.ws.vec; int* perm = P.ws.perm;
   const int tid = threadIdx.x;
   __shared__ int sh_gate;
@@ -444,7 +450,10 @@ int solve_from_moments(const double* M, const pdsb_solve_opts& o, double* beta, 
   P.ws.vec = d; d += 4 * (size_t)q + (size_t)q * o.t;
   P.ws.cs = d; d += 4 * (size_t)(q / 2 + 2);
   P.ws.perm = reinterpret_cast<int*>(d);
-  solve_kernel<<<1, NT, 0, s>>>(P);
+  const size_t hot = ((size_t)q * q + (size_t)q * nb) * sizeof(double);
+  P.use_smem = hot <= 200 * 1024;
+  if (P.use_smem && hot > 48 * 1024) cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot);
+  solve_kernel<<<1, NT, P.use_smem ? hot : 0, s>>>(P);
   cudaError_t e = cudaGetLastError();
   count_launch();
   dev_free(base, s);
