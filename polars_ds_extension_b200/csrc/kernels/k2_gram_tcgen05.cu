@@ -607,10 +607,14 @@ __global__ void __launch_bounds__((2 + 4 * NCONV + 4 * EPI_SETS) * 32, 1)
 gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ mask, int64_t n, int p, int t,
                           int zx, int zy, int64_t stages_total, double* __restrict__ partials /* [grid][128][N] */,
                           double* __restrict__ yside /* [grid][NCONV][4][3] */, const float* __restrict__ zbase, int64_t ld,
-                          int pf_dist) {
+                          int pf_dist, int blocked) {
   constexpr int N = NB * 16;
   constexpr int NH = N / EPI_SETS;
-  constexpr int RING = (NB == 4) ? 5 : V4_RING;
+  constexpr int RING = (NB == 4) ? 5 : (NB == 5 ? 4 : V4_RING);
+  // TMEM budget: two accumulator buffers of XD_COLS columns + XAB slots of 128 A columns (N = 80 leaves room for 2)
+  constexpr int XD_COLS = (NB <= 4) ? 64 : 80;
+  constexpr int XA_COL0 = 2 * XD_COLS;
+  constexpr int XAB = (NB <= 4) ? AB_STAGES : 2;
   constexpr int NTHREADS = (2 + 4 * NCONV + 4 * EPI_SETS) * 32;
   constexpr uint32_t TILE_BYTES = N * 128;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -630,7 +634,7 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < RING; ++i) { mbar_init(&bars->raw_full[i], 1); mbar_init(&bars->raw_empty[i], 1); }
-    for (int i = 0; i < AB_STAGES; ++i) { mbar_init(&bars->a_full[i], nquad); mbar_init(&bars->a_empty[i], 1); }
+    for (int i = 0; i < XAB; ++i) { mbar_init(&bars->a_full[i], nquad); mbar_init(&bars->a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->d_full[i], 1); mbar_init(&bars->d_empty[i], nquad * EPI_SETS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -663,8 +667,10 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
         mbar_arrive_expect_tx(&bars->raw_full[rs], (uint32_t)(BPS * q * 128));
         const int64_t row0 = STAGE_ROW0(it);
 #pragma unroll
-        for (int b = 0; b < BPS; ++b)
-          tma_load_2d(raw + ((size_t)rs * BPS + b) * TILE_BYTES, &tmap, &bars->raw_full[rs], (int)(row0 + b * BOX_ROWS), 0);
+        for (int b = 0; b < BPS; ++b) {
+          if (blocked) tma_load_3d(raw + ((size_t)rs * BPS + b) * TILE_BYTES, &tmap, &bars->raw_full[rs], b * BOX_ROWS, 0, (int)(row0 / STAGE_ROWS));
+          else tma_load_2d(raw + ((size_t)rs * BPS + b) * TILE_BYTES, &tmap, &bars->raw_full[rs], (int)(row0 + b * BOX_ROWS), 0);
+        }
       }
       __syncwarp();
       if (pf_dist > 0 && it + (uint32_t)pf_dist < my_stages) prefetch_stage(zbase, ld, q, STAGE_ROW0(it + pf_dist), n, lane);
@@ -680,8 +686,8 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
       mbar_wait(&bars->a_full[s], ph);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t d_addr = tmem + buf * D_COLS;
-        const uint32_t a_base = tmem + A_COL0 + s * A_SLOT_COLS;
+        const uint32_t d_addr = tmem + buf * XD_COLS;
+        const uint32_t a_base = tmem + XA_COL0 + s * A_SLOT_COLS;
         const uint64_t bd0 = make_b_desc(raw_addr + rs * (BPS * TILE_BYTES));
 #pragma unroll
         for (int b = 0; b < BPS; ++b) {
@@ -696,7 +702,7 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
         if (fl == FLUSH_STAGES - 1 || it == my_stages - 1) tc_commit(&bars->d_full[buf]);
       }
       __syncwarp();
-      if (++s == AB_STAGES) { s = 0; ph ^= 1; }
+      if (++s == XAB) { s = 0; ph ^= 1; }
       if (++rs == RING) rs = 0;
       if (++fl == FLUSH_STAGES) { fl = 0; if (buf) dph ^= 1; buf ^= 1; }
     }
@@ -715,7 +721,7 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
       double dsy = 0.0, dsyy = 0.0, dcnt = 0.0;
       for (uint32_t it = set; it < my_stages; it += NCONV) {
         const uint32_t rs = it % RING, rph = (it / RING) & 1;
-        const uint32_t s = it % AB_STAGES, sph = (it / AB_STAGES) & 1;
+        const uint32_t s = it % XAB, sph = (it / XAB) & 1;
         mbar_wait(&bars->raw_full[rs], rph);
         mbar_wait(&bars->a_empty[s], sph ^ 1);
         tc_fence_after();
@@ -777,7 +783,7 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
               v[k] = __float_as_uint(x - __uint_as_float(v[k] & 0xFFFFE000u));
             }
           }
-          tmem_st32(tmem + lane_addr + (uint32_t)(A_COL0 + s * A_SLOT_COLS + b * BOX_ROWS), v);
+          tmem_st32(tmem + lane_addr + (uint32_t)(XA_COL0 + s * A_SLOT_COLS + b * BOX_ROWS), v);
         }
         dsy += (double)sy; dsyy += (double)syy; sy = 0.0f; syy = 0.0f;
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -812,15 +818,18 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
       for (uint32_t g = 0; g < groups; ++g) {
         mbar_wait(&bars->d_full[buf], dph);
         tc_fence_after();
-        uint32_t v[NH];
+        // drain in chunks of 8 columns (keeps the register footprint flat for N = 80)
 #pragma unroll
-        for (int c = 0; c < NH / 8; ++c) tmem_ld8(tmem + lane_addr + (uint32_t)(buf * D_COLS + eset * NH + c * 8), v + 8 * c);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int c = 0; c < NH / 8; ++c) {
+          uint32_t v[8];
+          tmem_ld8(tmem + lane_addr + (uint32_t)(buf * XD_COLS + eset * NH + c * 8), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[c * 8 + j] += (double)__uint_as_float(v[j]);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->d_empty[buf]);
-#pragma unroll
-        for (int j = 0; j < NH; ++j) acc[j] += (double)__uint_as_float(v[j]);
         if (buf) dph ^= 1;
         buf ^= 1;
       }
@@ -932,7 +941,7 @@ struct Geometry { const float* base; int q; int zx, zy; bool ok; bool blocked; }
 
 Geometry analyse(const float* X, int64_t ldx, const float* Y, int64_t ldy, int p, int t) {
   Geometry g{nullptr, p + t, 0, 0, false, false};
-  if (p < 1 || t < 1 || p + t + 1 > 64) return g;
+  if (p < 1 || t < 1 || p > 64 || (p + t + 1 > 64 && p + 2 * t + 1 > 80) || t > 8) return g;
   if (ldx != ldy || (ldx % 4) != 0) return g;
   if (Y == X + (size_t)p * ldx) { g.base = X; g.zx = 0; g.zy = p; g.ok = true; }          // [X | Y]
   else if (X == Y + (size_t)t * ldy) { g.base = Y; g.zx = t; g.zy = 0; g.ok = true; }     // [Y | X]
@@ -1007,14 +1016,14 @@ void set_tc_mode(int m) { g_tc_mode.store(m); }
 
 template <int NB, int NCONV>
 int launch_xonly(const CUtensorMap& tmap, const float* mask, int64_t n, int p, int t, int zx, int zy, int64_t stages_total,
-                 int grid, double* partials, double* yside, const float* zbase, int64_t ld, cudaStream_t s) {
+                 int grid, double* partials, double* yside, const float* zbase, int64_t ld, int blocked, cudaStream_t s) {
   constexpr int N = NB * 16;
-  constexpr int RING = (NB == 4) ? 5 : V4_RING;
+  constexpr int RING = (NB == 4) ? 5 : (NB == 5 ? 4 : V4_RING);
   const size_t smem = (size_t)RING * BPS * N * 128 + sizeof(BarriersV4) + 256;
   auto k = gram_tcgen05_xonly_kernel<NB, NCONV>;
   PDSB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static int pf = [] { const char* e = getenv("PDSB_TC_PF"); return e ? atoi(e) : PF_DIST; }();
-  k<<<grid, (2 + 4 * NCONV + 4 * EPI_SETS) * 32, smem, s>>>(tmap, mask, n, p, t, zx, zy, stages_total, partials, yside, zbase, ld, pf);
+  k<<<grid, (2 + 4 * NCONV + 4 * EPI_SETS) * 32, smem, s>>>(tmap, mask, n, p, t, zx, zy, stages_total, partials, yside, zbase, ld, pf, blocked);
   PDSB_LAUNCH_OK();
   count_launch();
   return 0;
@@ -1045,7 +1054,7 @@ int moments_tcgen05_f32(const float* X, int64_t ldx, const float* Y, int64_t ldy
 // row-blocked frame: [block][column][FRAME_ROWS]; the frame holds exactly the p + t columns, X at xcol, Y at ycol
 bool moments_tcgen05_frame_supported(int64_t n, int ncols, int xcol, int p, int ycol, int t) {
   if (getenv("PDSB_DISABLE_TCGEN05") || !get_encode_fn()) return false;
-  if (n < 4096 || p < 1 || t < 1 || p + t + 1 > 64 || ncols != p + t) return false;
+  if (n < 4096 || p < 1 || t < 1 || p > 64 || (p + t + 1 > 64 && (p + 2 * t + 1 > 80 || t > 4)) || ncols != p + t) return false;
   return (xcol == 0 && ycol == p) || (ycol == 0 && xcol == t);
 }
 
@@ -1062,7 +1071,8 @@ static int moments_tcgen05_core(const Geometry& g, int64_t ldx, const float* mas
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return -1;
   const int q = g.q, qt = q + 1;
-  const bool xonly = (tc_mode() == 3) && !g.blocked && (p + 2 * t + 1 <= 64) && t <= 4;
+  // features-only A operand: chosen explicitly (variant 3) or whenever Z~ has more than 64 columns (p up to 64)
+  const bool xonly = ((tc_mode() == 3 && !g.blocked) || p + t + 1 > 64) && (p + 2 * t + 1 <= 80) && p <= 64 && t <= 4;
   const int N = xonly ? ((p + 2 * t + 1 + 15) / 16) * 16 : ((qt + 15) / 16) * 16;
   CUtensorMap tmap;
   CUresult cr;
@@ -1096,13 +1106,14 @@ static int moments_tcgen05_core(const Geometry& g, int64_t ldx, const float* mas
   const int q1 = p + t + 1;
   if (xonly) {
     const int nconv = xonly_nconv();
-#define PDSB_XO(NBV) (nconv == 3 ? launch_xonly<NBV, 3>(tmap, mask, n, p, t, g.zx, g.zy, stages_total, grid, partials, yside, g.base, ldx, s) \
-                                 : launch_xonly<NBV, 2>(tmap, mask, n, p, t, g.zx, g.zy, stages_total, grid, partials, yside, g.base, ldx, s))
+#define PDSB_XO(NBV) (nconv == 3 ? launch_xonly<NBV, 3>(tmap, mask, n, p, t, g.zx, g.zy, stages_total, grid, partials, yside, g.base, ldx, g.blocked ? 1 : 0, s) \
+                                 : launch_xonly<NBV, 2>(tmap, mask, n, p, t, g.zx, g.zy, stages_total, grid, partials, yside, g.base, ldx, g.blocked ? 1 : 0, s))
     switch (N / 16) {
       case 1: rc = PDSB_XO(1); break;
       case 2: rc = PDSB_XO(2); break;
       case 3: rc = PDSB_XO(3); break;
-      default: rc = PDSB_XO(4); break;
+      case 4: rc = PDSB_XO(4); break;
+      default: rc = PDSB_XO(5); break;
     }
 #undef PDSB_XO
     if (!rc) {

@@ -29,7 +29,8 @@ def _ref(X, Y, n, w=None, mask=None):
 
 @pytest.mark.parametrize("n,p,t,order", [(4096, 4, 1, "xy"), (100_003, 32, 1, "yx"), (1_000_000, 32, 1, "xy"),
                                          (50_000, 8, 3, "yx"), (65_536 * 3 + 17, 62, 1, "xy"), (200_000, 1, 1, "xy"),
-                                         (300_000, 14, 1, "xy"), (300_000, 15, 1, "xy"), (77_777, 47, 1, "yx")])
+                                         (300_000, 14, 1, "xy"), (300_000, 15, 1, "xy"), (77_777, 47, 1, "yx"),
+                                         (150_000, 64, 1, "yx")])
 def test_tcgen05_moments_vs_numpy(n, p, t, order):
     import torch
 
@@ -60,6 +61,8 @@ def test_tcgen05_moments_vs_numpy(n, p, t, order):
     assert err_tc < 3e-6, (err_tc, err_simt)
     assert err_simt < 3e-6, err_simt
     assert np.array_equal(M, M.T, equal_nan=True)
+    if p + t + 1 > 64:
+        return      # only the features-only kernel takes this shape (checked against numpy above)
     # the x-only-A variant (does not produce y_i . y_j for i != j: NaN there) must agree with the default kernel
     lib().pdsb_set_moments_path(2)
     lib().pdsb_set_tc_variant(3)
