@@ -1072,7 +1072,7 @@ static int moments_tcgen05_core(const Geometry& g, int64_t ldx, const float* mas
   if (!enc) return -1;
   const int q = g.q, qt = q + 1;
   // features-only A operand: chosen explicitly (variant 3) or whenever Z~ has more than 64 columns (p up to 64)
-  const bool xonly = ((tc_mode() == 3 && !g.blocked) || p + t + 1 > 64) && (p + 2 * t + 1 <= 80) && p <= 64 && t <= 4;
+  const bool xonly = (tc_mode() == 3 || p + t + 1 > 64) && (p + 2 * t + 1 <= 80) && p <= 64 && t <= 4;
   const int N = xonly ? ((p + 2 * t + 1 + 15) / 16) * 16 : ((qt + 15) / 16) * 16;
   CUtensorMap tmap;
   CUresult cr;
