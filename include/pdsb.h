@@ -155,6 +155,16 @@ int pdsb_dev_online_lin_reg_f64(const double* X, int64_t ldx, const double* y, i
                                 int64_t window, int64_t min_rows, int skip, double lambda, double* coeffs,
                                 double* pred, uint8_t* valid, void* stream);
 
+/* Row-sharded recursive_lin_reg: the shard holding global rows [row0, row0 + n) continues the
+ * expanding fit of the shards before it.  m0 = moments [X | y | 1]' [X | y | 1] ((p+2)^2 f64, row-major, as written by
+ * pdsb_dev_moments_* with t = 1) summed over all preceding rows (null for the first shard). */
+int pdsb_dev_recursive_shard_f32(const float* X, int64_t ldx, const float* y, int64_t n, int p, int add_bias,
+                                 int64_t min_rows, int skip, double lambda, const double* m0, int64_t row0,
+                                 float* coeffs, float* pred, uint8_t* valid, void* stream);
+int pdsb_dev_recursive_shard_f64(const double* X, int64_t ldx, const double* y, int64_t n, int p, int add_bias,
+                                 int64_t min_rows, int skip, double lambda, const double* m0, int64_t row0,
+                                 double* coeffs, double* pred, uint8_t* valid, void* stream);
+
 /* lin_reg_report statistics (pl_lin_reg_report / pl_wls_report, linear_regression.rs:822-1117).
  * se_type: 0 se, 1..4 hc0..hc3.  out: 8 rows x (p+bias) f64 row-major = beta, std_err, t, p, ci_lo, ci_hi,
  * and r2 / adj_r2 broadcast.  y_var is the ddof=1 variance Polars computes upstream (expr_linear.py:615). */

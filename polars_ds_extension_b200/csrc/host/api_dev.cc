@@ -124,14 +124,29 @@ int pdsb_dev_online_lin_reg_f32(const float* X, int64_t ldx, const float* y, int
                                 int64_t window, int64_t min_rows, int skip, double lambda, float* coeffs,
                                 float* pred, uint8_t* valid, void* stream) {
   if (require_device()) return 1;
-  return online_lin_reg<float>(X, ldx, y, n, p, add_bias, window, min_rows, skip, lambda, coeffs, pred, valid,
+  return online_lin_reg<float>(X, ldx, y, n, p, add_bias, window, min_rows, skip, lambda, nullptr, 0, coeffs, pred, valid,
                                (cudaStream_t)stream);
 }
 int pdsb_dev_online_lin_reg_f64(const double* X, int64_t ldx, const double* y, int64_t n, int p, int add_bias,
                                 int64_t window, int64_t min_rows, int skip, double lambda, double* coeffs,
                                 double* pred, uint8_t* valid, void* stream) {
   if (require_device()) return 1;
-  return online_lin_reg<double>(X, ldx, y, n, p, add_bias, window, min_rows, skip, lambda, coeffs, pred, valid,
+  return online_lin_reg<double>(X, ldx, y, n, p, add_bias, window, min_rows, skip, lambda, nullptr, 0, coeffs, pred, valid,
+                                (cudaStream_t)stream);
+}
+
+int pdsb_dev_recursive_shard_f32(const float* X, int64_t ldx, const float* y, int64_t n, int p, int add_bias,
+                                 int64_t min_rows, int skip, double lambda, const double* m0, int64_t row0,
+                                 float* coeffs, float* pred, uint8_t* valid, void* stream) {
+  if (require_device()) return 1;
+  return online_lin_reg<float>(X, ldx, y, n, p, add_bias, 0, min_rows, skip, lambda, m0, row0, coeffs, pred, valid,
+                               (cudaStream_t)stream);
+}
+int pdsb_dev_recursive_shard_f64(const double* X, int64_t ldx, const double* y, int64_t n, int p, int add_bias,
+                                 int64_t min_rows, int skip, double lambda, const double* m0, int64_t row0,
+                                 double* coeffs, double* pred, uint8_t* valid, void* stream) {
+  if (require_device()) return 1;
+  return online_lin_reg<double>(X, ldx, y, n, p, add_bias, 0, min_rows, skip, lambda, m0, row0, coeffs, pred, valid,
                                 (cudaStream_t)stream);
 }
 

@@ -437,7 +437,7 @@ int host_online_t(const pdsb_column* cols, int n_cols, const pdsb_lr_kwargs* kw,
   if (!dco || !dpr || !dva) return 1;
   const int64_t window = rolling ? kw->n : 0;
   const int64_t min_rows = rolling ? kw->min_size : kw->n;
-  if (online_lin_reg<T>(F.X(), F.ld, F.Y(), F.n, F.p, add_bias, window, min_rows, skip, kw->lambda, dco, dpr, dva, s)) return 1;
+  if (online_lin_reg<T>(F.X(), F.ld, F.Y(), F.n, F.p, add_bias, window, min_rows, skip, kw->lambda, nullptr, 0, dco, dpr, dva, s)) return 1;
   memset(out, 0, sizeof(*out));
   out->is_f32 = sizeof(T) == 4; out->n_coef = q; out->n_targets = 1; out->n_rows = F.n;
   out->coeffs = result_buf(out, (size_t)F.n * q * sizeof(T));

@@ -35,7 +35,8 @@ namespace pdsb {
 
 namespace {
 
-constexpr int WARPS = 4;                 // independent chains per CTA (no block-level synchronisation anywhere)
+constexpr int WARPS = 5;                 // independent chains per CTA (no block-level synchronisation anywhere);
+                                         // 3 CTAs x 5 warps fit the 8-feature + bias f32 case in shared memory and registers
 constexpr int CTA_THREADS = WARPS * 32;
 constexpr int BATCH = 32;                // rows per role switch
 constexpr int CHAIN_ROWS = 1024;         // rows per warp = granularity of the prefix arrays
@@ -93,8 +94,12 @@ template <typename T, int D>
 __device__ __forceinline__ void load_raw(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y, int p,
                                          int64_t r, int64_t n, T* z, T& yv) {
   const int64_t rc = min(max(r, (int64_t)0), n - 1);
+  const T* q = X + rc;
 #pragma unroll
-  for (int c = 0; c < D; ++c) z[c] = (c < p) ? __ldg(X + (int64_t)c * ldx + rc) : T(1);
+  for (int c = 0; c < D; ++c) {
+    if (c < p) { z[c] = __ldg(q); q += ldx; }
+    else z[c] = T(1);
+  }
   yv = __ldg(y + rc);
 }
 
@@ -106,8 +111,8 @@ __device__ __forceinline__ bool put_row(double* __restrict__ dst, const T* z, T 
   for (int c = 0; c < D; ++c) acc = fma(z[c], T(0), acc);     // 0 when every entry is finite, NaN otherwise
   const bool fin = inr && (acc == T(0));
 #pragma unroll
-  for (int c = 0; c < D; ++c) dst[c] = fin ? (double)z[c] : 0.0;
-  dst[D] = fin ? (double)yv : 0.0;
+  for (int c = 0; c < D; ++c) dst[c] = (double)(fin ? z[c] : T(0));
+  dst[D] = (double)(fin ? yv : T(0));
   dst[D + 1] = fin ? 1.0 : 0.0;
   if (((D + 1) | 1) != D + 1) dst[(D + 1) | 1] = 0.0;
   return fin;
@@ -119,7 +124,7 @@ __device__ __forceinline__ void walk_batch(const double* __restrict__ ee, const 
                                            const int* ta, const int* tb, const int* k0, const int* k1,
                                            double (*W)[2], T* __restrict__ gs, double* __restrict__ cnt, bool cnt_lane) {
   constexpr int ES = MomN<D>::ES, GS = MomN<D>::GS, TPL = MomN<D>::TPL, NT = MomN<D>::NT;
-#pragma unroll 4
+#pragma unroll
   for (int r = 0; r < BATCH; ++r) {
     const double* e = ee + r * ES;
     const double* l = el + r * ES;
@@ -193,11 +198,27 @@ chain_sums_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y,
 }
 
 // ---------------- pass B: exclusive scan along tiles, one block per component ----------------
-__global__ void __launch_bounds__(1024) tile_scan_kernel(double* __restrict__ S, int64_t ntiles) {
+// M0 (optional): moments [X | y | 1]' [X | y | 1] ((p+2)^2, row-major f64) of the rows that precede this shard; they
+// seed the prefix so that a row shard continues the expanding fit of the shards before it.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(double* __restrict__ S, int64_t ntiles,
+                                                         const double* __restrict__ M0, int p, int d) {
   __shared__ double warp_tot[32];
   __shared__ double carry;
   double* row = S + (size_t)blockIdx.x * ntiles;
-  if (threadIdx.x == 0) carry = 0.0;
+  if (threadIdx.x == 0) {
+    double c0 = 0.0;
+    if (M0) {
+      // component blockIdx.x -> (i, j) over (z_0..z_{d-1}, y, 1);  z_c = x_c for c < p, the ones column otherwise
+      const int ng = d * (d + 1) / 2;
+      int c = blockIdx.x, i, j;
+      if (c >= ng + d) { i = j = d + 1; }
+      else if (c >= ng) { i = c - ng; j = d; }
+      else { i = 0; while (c >= d - i) { c -= d - i; ++i; } j = i + c; }
+      auto col = [&](int a) { return a < p ? a : (a == d ? p : p + 1); };   // y -> p, bias / ones -> p + 1
+      c0 = M0[(size_t)col(i) * (p + 2) + col(j)];
+    }
+    carry = c0;
+  }
   __syncthreads();
   for (int64_t base = 0; base < ntiles; base += blockDim.x) {
     int64_t i = base + threadIdx.x;
@@ -263,7 +284,7 @@ __device__ __forceinline__ bool chol_solve_packed(T* g, T lambda, T* beta) {
 template <typename T, int D>
 __global__ void __launch_bounds__(CTA_THREADS)
 online_main_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y, int64_t n, int p,
-                   int64_t window, int64_t min_rows, int skip, T lambda, int64_t nchains,
+                   int64_t window, int64_t min_rows, int skip, T lambda, int64_t row0, int64_t nchains,
                    const double* __restrict__ C /* [NM][nchains] exclusive chain prefixes */,
                    T* __restrict__ coeffs, T* __restrict__ pred, uint8_t* __restrict__ valid) {
   constexpr int NM = MomN<D>::NM, ES = MomN<D>::ES, GS = MomN<D>::GS, TPL = MomN<D>::TPL, NT = MomN<D>::NT;
@@ -340,7 +361,7 @@ online_main_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y
     __syncwarp();
     bool ok;
     if (rolling) ok = (r >= window - 1) && (!skip || cn >= (double)min_rows - 0.5);
-    else ok = skip ? (fin && cn >= (double)min_rows - 0.5) : (r >= min_rows - 1);
+    else ok = skip ? (fin && cn >= (double)min_rows - 0.5) : (r + row0 >= min_rows - 1);
     T beta[D];
     T pr = T(0);
     if (ok) {
@@ -369,7 +390,7 @@ online_main_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y
 
 template <typename T, int D>
 int run_online(const T* X, int64_t ldx, const T* y, int64_t n, int p, int64_t window, int64_t min_rows, int skip,
-               double lambda, T* coeffs, T* pred, uint8_t* valid, cudaStream_t s) {
+               double lambda, const double* m0, int64_t row0, T* coeffs, T* pred, uint8_t* valid, cudaStream_t s) {
   constexpr int NM = MomN<D>::NM;
   const int64_t nchains = ceil_div(n, CHAIN_ROWS);
   double* S = nullptr;
@@ -381,9 +402,9 @@ int run_online(const T* X, int64_t ldx, const T* y, int64_t n, int p, int64_t wi
   const unsigned grid = (unsigned)ceil_div(nchains, WARPS);
   ka<<<grid, CTA_THREADS, 0, s>>>(X, ldx, y, n, p, nchains, S);
   cudaError_t e = cudaGetLastError(); count_launch();
-  if (e == cudaSuccess) { tile_scan_kernel<<<NM, 1024, 0, s>>>(S, nchains); e = cudaGetLastError(); count_launch(); }
+  if (e == cudaSuccess) { tile_scan_kernel<<<NM, 1024, 0, s>>>(S, nchains, m0, p, D); e = cudaGetLastError(); count_launch(); }
   if (e == cudaSuccess) {
-    kc<<<grid, CTA_THREADS, smem, s>>>(X, ldx, y, n, p, window, min_rows, skip, (T)lambda, nchains, S, coeffs, pred, valid);
+    kc<<<grid, CTA_THREADS, smem, s>>>(X, ldx, y, n, p, window, min_rows, skip, (T)lambda, row0, nchains, S, coeffs, pred, valid);
     e = cudaGetLastError(); count_launch();
   }
   dev_free(S, s);
@@ -395,11 +416,13 @@ int run_online(const T* X, int64_t ldx, const T* y, int64_t n, int p, int64_t wi
 
 template <typename T>
 int online_lin_reg(const T* X, int64_t ldx, const T* y, int64_t n, int p, int add_bias, int64_t window,
-                   int64_t min_rows, int skip, double lambda, T* coeffs, T* pred, uint8_t* valid, cudaStream_t s) {
+                   int64_t min_rows, int skip, double lambda, const double* m0, int64_t row0, T* coeffs, T* pred,
+                   uint8_t* valid, cudaStream_t s) {
   if (n <= 0) return 0;
+  if (window > 0 && m0) { set_error("online lin_reg: preceding-row moments only apply to the recursive fit"); return 1; }
   const int d = p + (add_bias ? 1 : 0);
   if (n / CHAIN_ROWS > 2000000000LL) { set_error("online lin_reg: too many rows"); return 1; }
-#define CASE_D(DD) case DD: return run_online<T, DD>(X, ldx, y, n, p, window, min_rows, skip, lambda, coeffs, pred, valid, s);
+#define CASE_D(DD) case DD: return run_online<T, DD>(X, ldx, y, n, p, window, min_rows, skip, lambda, m0, row0, coeffs, pred, valid, s);
   switch (d) {
     CASE_D(1) CASE_D(2) CASE_D(3) CASE_D(4) CASE_D(5) CASE_D(6) CASE_D(7) CASE_D(8) CASE_D(9) CASE_D(10)
     CASE_D(11) CASE_D(12)
@@ -411,8 +434,8 @@ int online_lin_reg(const T* X, int64_t ldx, const T* y, int64_t n, int p, int ad
 }
 
 template int online_lin_reg<float>(const float*, int64_t, const float*, int64_t, int, int, int64_t, int64_t, int,
-                                   double, float*, float*, uint8_t*, cudaStream_t);
+                                   double, const double*, int64_t, float*, float*, uint8_t*, cudaStream_t);
 template int online_lin_reg<double>(const double*, int64_t, const double*, int64_t, int, int, int64_t, int64_t, int,
-                                    double, double*, double*, uint8_t*, cudaStream_t);
+                                    double, const double*, int64_t, double*, double*, uint8_t*, cudaStream_t);
 
 }  // namespace pdsb

@@ -61,8 +61,8 @@ int grouped_lin_reg(const T* X, int64_t ldx, const T* y, const int64_t* offsets,
 // K6/K7 rolling + recursive
 template <typename T>
 int online_lin_reg(const T* X, int64_t ldx, const T* y, int64_t n, int p, int add_bias, int64_t window,
-                   int64_t min_rows, int skip, double lambda, T* coeffs, T* pred, uint8_t* valid,
-                   cudaStream_t s);
+                   int64_t min_rows, int skip, double lambda, const double* m0 /* moments of the preceding rows or null */,
+                   int64_t row0 /* global index of row 0 */, T* coeffs, T* pred, uint8_t* valid, cudaStream_t s);
 
 // K9 report
 template <typename T>

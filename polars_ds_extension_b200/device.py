@@ -109,6 +109,23 @@ def online_lin_reg(X: torch.Tensor, y: torch.Tensor, window: int, min_rows: int,
     return coeffs, pred, valid
 
 
+def recursive_shard(X: torch.Tensor, y: torch.Tensor, min_rows: int, m0: Optional[torch.Tensor], row0: int,
+                    add_bias: bool = False, l2_reg: float = 0.0, skip: bool = False):
+    """recursive_lin_reg on the row shard that starts at global row `row0`; `m0` = float64 (p+2)^2 moments
+    ([X | y | 1]) of all preceding rows (None for the first shard)."""
+    p, n = X.shape
+    q = p + int(add_bias)
+    coeffs = torch.empty((n, q), dtype=X.dtype, device=X.device)
+    pred = torch.empty(n, dtype=X.dtype, device=X.device)
+    valid = torch.empty(n, dtype=torch.uint8, device=X.device)
+    if m0 is not None:
+        assert m0.dtype == torch.float64 and m0.is_contiguous() and m0.numel() == (p + 2) ** 2
+    fn = getattr(lib(), f"pdsb_dev_recursive_shard_{_sfx(X)}")
+    check(fn(_ptr(X), _ld(X), _ptr(y), n, p, int(add_bias), min_rows, int(skip), float(l2_reg),
+             _ptr(m0) if m0 is not None else None, row0, _ptr(coeffs), _ptr(pred), _ptr(valid), _stream()))
+    return coeffs, pred, valid
+
+
 FRAME_ROWS = 128
 
 

@@ -27,3 +27,40 @@ def allreduce_moments(M: torch.Tensor) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(M, op=dist.ReduceOp.SUM)
     return M
+
+
+def shard_groups(offsets, rank: int, world: int) -> Tuple[int, int]:
+    """group_by: groups are independent, so ranks take contiguous group ranges balanced by ROW count; no collective on
+    the data path.  `offsets` = the n_groups + 1 group boundaries of the key-sorted frame.  Returns the
+    [g0, g1) group range of `rank`."""
+    import numpy as np
+
+    off = np.asarray(offsets, dtype=np.int64)
+    n_groups = len(off) - 1
+    if n_groups <= 0:
+        return 0, 0
+    total = int(off[-1] - off[0])
+    # boundary r = first group whose start reaches r/world of the rows; monotone, covers every group exactly once
+    cuts = [int(np.searchsorted(off[:-1] - off[0], (total * r) // world, side="left")) for r in range(world)] + [n_groups]
+    cuts[0] = 0
+    return cuts[rank], max(cuts[rank], cuts[rank + 1])
+
+
+def rolling_halo(begin: int, window: int) -> int:
+    """rolling_lin_reg on a row shard [begin, end): the shard also reads the `window - 1` rows before `begin`
+    (a read-only overlap with its left neighbour, no collective); the outputs of the halo rows are dropped."""
+    return min(begin, max(window - 1, 0))
+
+
+def exclusive_prefix_moments(M: torch.Tensor) -> torch.Tensor:
+    """recursive_lin_reg on row shards: every rank needs the moments of all rows before its shard.  One all-gather of the
+    per-shard totals ((p+2)^2 float64 each), then a local sum over the lower ranks (deterministic order)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return torch.zeros_like(M)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    parts = [torch.empty_like(M) for _ in range(world)]
+    dist.all_gather(parts, M.contiguous())
+    out = torch.zeros_like(M)
+    for r in range(rank):
+        out += parts[r]
+    return out
