@@ -41,7 +41,7 @@ def test_recursive_shards_continue_the_prefix(dtype_name, n, p, bias, world):
         ok = va.bool()
         tol = 2e-4 if dtype == torch.float32 else 1e-9
         assert torch.allclose(co[ok], full[0][b:e][ok], rtol=tol, atol=tol)
-        assert torch.allclose(pr[ok], full[1][b:e][ok], rtol=tol, atol=tol)
+        assert torch.allclose(pr[ok], full[1][b:e][ok], rtol=tol, atol=tol, equal_nan=True)
         # what the next rank receives: moments of the finite rows seen so far (exclusive_prefix_moments in parallel.py)
         prefix = prefix + dev.moments(Zc[:p, b:e], Zc[p:p + 1, b:e], mask=fin[b:e].to(dtype).contiguous())
     assert int(full[2].sum()) == n - (min_rows - 1)
