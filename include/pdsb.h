@@ -243,6 +243,40 @@ int pdsb_host_online(const pdsb_column* cols, int n_cols, const pdsb_lr_kwargs* 
 int pdsb_host_grouped_lin_reg(const pdsb_column* cols, int n_cols, const int64_t* group_offsets,
                               int64_t n_groups, const pdsb_lr_kwargs* kw, int f32, pdsb_host_result* out);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Dense-matrix callers of the same solvers: what the reference's PyO3 classes bind
+ * (src/pymodels/py_lr.rs:21-224: PyLR, PyElasticNet, PyOnlineLR; numpy float64 matrices, numpy_faer.rs:10-66).
+ * A pdsb_matrix is a HOST view with strides in elements.  Accepted layouts: C order (col_stride == 1),
+ * F order (row_stride == 1), and any strided column vector; anything else -> "Input array is not contiguous."
+ * Error strings follow LinalgErrors::to_string (src/linear/mod.rs:20-31).
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct pdsb_matrix {
+  const double* data;
+  int64_t n_rows, n_cols;
+  int64_t row_stride, col_stride;
+} pdsb_matrix;
+
+enum pdsb_model { PDSB_MODEL_LR = 0, PDSB_MODEL_ELASTIC_NET = 1, PDSB_MODEL_ONLINE_LR = 2 };
+
+/* LR::fit (lr_solvers.rs:64-73: faer_solve_lr, ungated; l2_reg = lambda on the non-bias diagonal; `solver` as
+ * lr/mod.rs:18-27), ElasticNet::fit (:140-176: coordinate descent, l1/l2 scaled by n inside, tol, max_iter),
+ * OnlineLR::fit (lr_online_solvers.rs:100-143: QR solve + explicit inverse of X'X + lambda I).
+ * coeffs: n_cols + add_bias doubles, bias last.  inv (PDSB_MODEL_ONLINE_LR only): (n_cols + add_bias)^2, row-major. */
+int pdsb_model_fit(int model, const pdsb_matrix* X, const pdsb_matrix* y, int add_bias, const char* solver,
+                   double l1_reg, double l2_reg, double tol, int64_t max_iter, double* coeffs, double* inv);
+/* LinearModel::predict (lr/mod.rs:146-174): out[r] = X[r,:] . coeffs[:p] + (has_bias ? coeffs[p] : 0) */
+int pdsb_model_predict(const pdsb_matrix* X, const double* coeffs, int n_coef, int has_bias, double* out);
+
+/* OnlineLR state ((X'X)^-1 and the coefficients) kept resident on the device between updates. */
+typedef struct pdsb_online_lr pdsb_online_lr;
+pdsb_online_lr* pdsb_online_lr_new(int n_coef, int has_bias);          /* NULL on failure (see pdsb_last_error) */
+void pdsb_online_lr_free(pdsb_online_lr* h);
+int pdsb_online_lr_set(pdsb_online_lr* h, const double* coeffs, const double* inv);   /* set_coeffs_bias_inverse :29-52 */
+/* OnlineLR::update (:85-89) + woodbury_step (:307-332); c = +1 adds the row, -1 removes it.  A row with a
+ * non-finite value is ignored.  Stream-ordered: returns without waiting for the device. */
+int pdsb_online_lr_update(pdsb_online_lr* h, const double* x_row, double y, double c);
+int pdsb_online_lr_get(pdsb_online_lr* h, double* coeffs /* nullable */, double* inv /* nullable */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,13 @@ class SolveOpts(C.Structure):
     ]
 
 
+class Matrix(C.Structure):
+    """pdsb_matrix: a host float64 view, strides in elements."""
+    _fields_ = [("data", C.c_void_p), ("n_rows", C.c_int64), ("n_cols", C.c_int64),
+                ("row_stride", C.c_int64), ("col_stride", C.c_int64)]
+
+
+MODEL_LR, MODEL_ELASTIC_NET, MODEL_ONLINE_LR = range(3)
 METHOD_LSTSQ, METHOD_CD, METHOD_NNLS, METHOD_RCOND, METHOD_INV = range(5)
 SOLVER_QR, SOLVER_SVD, SOLVER_CHOLESKEY = range(3)
 
@@ -67,6 +74,16 @@ def lib() -> C.CDLL:
     L.pdsb_dev_moments_frame_f32.argtypes = [vp, i64, ci, ci, ci, ci, ci, vp, vp, vp]
     L.pdsb_dev_predict_frame_f32.argtypes = [vp, i64, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, i64, vp, vp, vp]
     L.pdsb_set_tc_variant.argtypes = [ci]
+    mp = C.POINTER(Matrix)
+    L.pdsb_model_fit.argtypes = [ci, mp, mp, ci, C.c_char_p, dbl, dbl, dbl, i64, vp, vp]
+    L.pdsb_model_predict.argtypes = [mp, vp, ci, ci, vp]
+    L.pdsb_online_lr_new.restype = vp
+    L.pdsb_online_lr_new.argtypes = [ci, ci]
+    L.pdsb_online_lr_free.argtypes = [vp]
+    L.pdsb_online_lr_free.restype = None
+    L.pdsb_online_lr_set.argtypes = [vp, vp, vp]
+    L.pdsb_online_lr_update.argtypes = [vp, vp, dbl, dbl]
+    L.pdsb_online_lr_get.argtypes = [vp, vp, vp]
     _lib = L
     return L
 

@@ -28,9 +28,11 @@ SOURCES = [
     "kernels/k5_grouped.cu",
     "kernels/k6_online.cu",
     "kernels/k9_report.cu",
+    "kernels/k10_models.cu",
     "host/context.cc",
     "host/api_dev.cc",
     "host/lr_host.cc",
+    "host/models_host.cc",
     "abi/plugin.cc",
 ]
 

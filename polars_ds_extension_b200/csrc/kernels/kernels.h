@@ -64,6 +64,13 @@ int online_lin_reg(const T* X, int64_t ldx, const T* y, int64_t n, int p, int ad
                    int64_t min_rows, int skip, double lambda, const double* m0 /* moments of the preceding rows or null */,
                    int64_t row0 /* global index of row 0 */, T* coeffs, T* pred, uint8_t* valid, cudaStream_t s);
 
+// K10 dense-matrix callers (model classes): strided gather to column-major, strided predict, Woodbury update
+template <typename T>
+int gather_colmajor(const T* src, int64_t rs, int64_t cs, int64_t n, int p, T* dst, int64_t ld, cudaStream_t s);
+int predict_strided(const double* X, int64_t rs, int64_t cs, int64_t n, int p, const double* beta, int has_bias,
+                    double* out, cudaStream_t s);
+int woodbury_update(double* inv, double* w, int q, int has_bias, const double* x, double y, double c, cudaStream_t s);
+
 // K9 report
 template <typename T>
 int report_stats(const T* X, int64_t ldx, const T* y, const T* w, const T* mask, int64_t n, int p,

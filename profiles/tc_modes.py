@@ -35,5 +35,5 @@ for _ in range(10):
     run()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
-print(f"variant={os.environ.get('PDSB_TC_MODE','1')} dbg={os.environ.get('PDSB_TC_DBG','0')} frame={int(use_frame)} max_rel_err={err.max():.3e} "
+print(f"variant={os.environ.get('PDSB_TC_MODE','1')} ring={os.environ.get('PDSB_TC_RING','0')} dbg={os.environ.get('PDSB_TC_DBG','0')} frame={int(use_frame)} max_rel_err={err.max():.3e} "
       f"ms(5e7 rows)={ms:.3f} GB/s={big*(p+1)*4/ms/1e6:.0f}")
