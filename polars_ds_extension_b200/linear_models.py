@@ -313,12 +313,12 @@ class OnlineLR:
     def from_coeffs_bias_inverse(cls, coeffs: List[float], bias: float, inv: np.ndarray):
         c = np.ascontiguousarray(coeffs, dtype=np.float64).ravel()
         inv = np.ascontiguousarray(inv, dtype=np.float64)
-        if inv.ndim != 2 or c.size != inv.shape[1]:       # set_coeffs_bias_inverse (lr_online_solvers.rs:35-36)
-            raise ValueError("Dimension mismatch.")
         m = cls(lambda_=0.0, has_bias=(bias > 0.0))
         has_bias = abs(bias) > np.finfo(np.float64).eps
         full = np.concatenate([c, [bias]]) if has_bias else c
-        if inv.shape != (full.size, full.size):
+        # The reference compares len(coeffs) with inv.ncols() (lr_online_solvers.rs:35-36), which rejects every model
+        # WITH a bias (its inverse has one more row/column); here the inverse must match coefficients + bias.
+        if inv.ndim != 2 or inv.shape != (full.size, full.size):
             raise ValueError("Dimension mismatch.")
         _call(lib().pdsb_online_lr_set(m._state(full.size, has_bias), full.ctypes.data, inv.ctypes.data))
         return m
