@@ -12,6 +12,7 @@ from .exprs.expr_linear import (  # noqa: F401
     lin_reg_w_rcond,
     recursive_lin_reg,
     rolling_lin_reg,
+    simple_lin_reg,
 )
 from .frame import Frame, col  # noqa: F401
 from ._lib import PdsbError, lib  # noqa: F401

@@ -18,7 +18,7 @@ from .. import config as cfg
 from ..frame import ColExpr, PluginExpr, col
 from ..typing import LRSolverMethods, NullPolicy
 
-__all__ = ["lin_reg", "lin_reg_w_rcond", "recursive_lin_reg", "rolling_lin_reg", "lin_reg_report"]
+__all__ = ["lin_reg", "simple_lin_reg", "lin_reg_w_rcond", "recursive_lin_reg", "rolling_lin_reg", "lin_reg_report"]
 
 ExprLike = Union[str, ColExpr]
 
@@ -86,6 +86,15 @@ def lin_reg(
     if return_pred:
         return PluginExpr(cfg._which_lin_reg("pl_lr_pred"), cols, kwargs, out_name="lr_pred")
     return PluginExpr(cfg._which_lin_reg("pl_lr"), cols, kwargs, returns_scalar=True, out_name="coeffs")
+
+
+def simple_lin_reg(x: ExprLike, target: ExprLike, add_bias: bool = False, weights: ExprLike | None = None,
+                   return_pred: bool = False) -> PluginExpr:
+    """One predictor, one target (reference: expr_linear.py:44-102, where the closed form beta = cov(x, y) / var(x),
+    alpha = mean(y) - beta mean(x) is spelled out of Polars reductions, several passes over the columns).  Here it is
+    the p = 1 case of the engine: one pass builds the 3 x 3 moments, the 1 x 1 / 2 x 2 solve is the same closed form.
+    No rank gate (a constant x gives what 0 / 0 gives in the closed form: no finite coefficients)."""
+    return lin_reg(x, target=target, add_bias=add_bias, weights=weights, return_pred=return_pred, singular_x_tol=0.0)
 
 
 def lin_reg_w_rcond(*x: ExprLike, target: ExprLike, add_bias: bool = False, rcond: float = 0.0, l2_reg: float = 0.0,

@@ -140,3 +140,32 @@ def test_models_match_the_oracle_and_report_errors():
     np.testing.assert_allclose(f.coeffs(), m.coeffs(), atol=1e-12)
     out = f.predict_df(df, name="yhat")
     np.testing.assert_allclose(np.asarray(out["yhat"].to_numpy()), m.predict(X).ravel(), atol=1e-12)
+
+
+@pytest.mark.parametrize("add_bias", [False, True])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_simple_lin_reg_is_the_closed_form(add_bias, weighted):
+    """`pds.simple_lin_reg` (expr_linear.py:44-102): beta = cov_w(x, y) / var_w(x), alpha = mean_w(y) - beta mean_w(x)."""
+    import polars_ds_extension_b200 as pds
+
+    rng = np.random.default_rng(21)
+    n = 20_000
+    x = rng.standard_normal(n) * 2.0 + 1.0
+    y = 0.75 * x - 0.4 + 0.3 * rng.standard_normal(n)
+    w = rng.random(n) + 0.1
+    ww = w if weighted else np.ones(n)
+    if add_bias:
+        xm, ym = np.sum(ww * x) / ww.sum(), np.sum(ww * y) / ww.sum()
+        beta = np.sum(ww * (x - xm) * (y - ym)) / np.sum(ww * (x - xm) ** 2)
+        want = [beta, ym - beta * xm]
+    else:
+        want = [np.sum(ww * x * y) / np.sum(ww * x * x)]
+    df = pds.Frame({"x": x, "y": y, "w": w})
+    e = pds.simple_lin_reg("x", "y", add_bias=add_bias, weights="w" if weighted else None)
+    got = df.select(e)["coeffs"][0].as_py()
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-11)
+    pr = df.select(pds.simple_lin_reg("x", "y", add_bias=add_bias, weights="w" if weighted else None, return_pred=True))
+    arr = pr["lr_pred"]
+    arr = arr.combine_chunks() if hasattr(arr, "combine_chunks") else arr
+    pred = np.asarray(arr.field("pred").to_numpy(zero_copy_only=False))
+    np.testing.assert_allclose(pred, want[0] * x + (want[1] if add_bias else 0.0), rtol=1e-9, atol=1e-9)
