@@ -60,15 +60,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // bounded spin: a protocol bug must surface as a trapped kernel (an error the host reports), never as a hung GPU
+  // bounded spin: a protocol bug must surface as a trapped kernel (an error the host reports), never as a hung GPU.
+  // The suspend-time hint lets the hardware park the warp until the phase flips instead of re-issuing the poll:
+  // ncu counted ~195 barrier polls per 128-row stage without it, all of them wavefronts on the shared-memory pipe.
   uint32_t done = 0;
   for (uint32_t spins = 0; !done; ++spins) {
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P1;\n\t"
-        "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
     if (!done && spins > (1u << 24)) __trap();
   }
 }
