@@ -267,6 +267,10 @@ def main():
     torch.cuda.synchronize()
     k_ms = ev0.elapsed_time(ev1) / reps
     alg_bytes = rows * (p + 1) * 4
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload, from the committed
+    # `ncu --set full` capture (profiles/gram_tcgen05_r01_ncu_metrics.csv: 13.200198 GB + 3.690496 MB); only valid for
+    # the default shape, null otherwise
+    traffic = 13_203_888_496 if (rows == 100_000_000 and p == 32 and path == 1) else None
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
@@ -316,7 +320,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "moments (Gram X'X | X'y)", "kernel_ms": k_ms,
+                         "traffic": traffic, "kernel": "moments (Gram X'X | X'y)", "kernel_ms": k_ms,
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
             "cpu_baseline": cpu,
         }

@@ -6,7 +6,7 @@
 # 3) launch lists of the other configs' kernels (grouped, rolling, recursive)
 set -x
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_r01.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_r01.csv \
     python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gram_tcgen05 -s 3 -c 1 -o gpurun_out/prof_gram_r01 -f \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/prof_gram_r01.log 2>&1
