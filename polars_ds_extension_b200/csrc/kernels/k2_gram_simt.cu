@@ -7,9 +7,11 @@
 // This is the path for f64 data, weighted fits, tiny inputs and shapes the tcgen05 kernel does not take
 // (k2_gram_tcgen05.cu is the f32 headline path).  Layout: X col-major [n x p] (ldx), Y col-major [n x t] (ldy).
 // Each CTA walks row tiles of TILE_R rows: tile -> shared memory (row-major, row stride S), every thread owns
-// up to MAXT 4x4 blocks of the upper triangle; per tile the block is accumulated in T (a TILE_R-long FMA chain)
-// and then added to f64 accumulators, so f32 rounding never grows with n.  Per-CTA partials are reduced in a
-// fixed order by a second kernel -> bit-reproducible results.
+// up to MAXT 4x4 blocks of the upper triangle; per tile the block is accumulated in T (a short FMA chain)
+// and then added to f64 accumulators, so f32 rounding never grows with n.  When there are fewer blocks than threads
+// (q1 <= 88, the usual case) the 256 threads are dealt as (block, row slice): 256 / #blocks slices each take every
+// nslices-th row of the tile, so all threads work (with one thread per block only 45 of 256 had work at q1 = 34).
+// Per-(CTA, slice) partials are reduced in a fixed order by a second kernel -> bit-reproducible results.
 #include "../common.h"
 #include "kernels.h"
 
@@ -31,13 +33,15 @@ gram_simt_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ Y, 
   const int ntp = nt * (nt + 1) / 2;
   const int tid = threadIdx.x;
 
-  // tile-pair decode for this thread
+  // (block, row slice) decode for this thread; more than 256 blocks -> MAXT blocks per thread, one slice
+  const int nslices = (MAXT == 1 && ntp <= 256) ? 256 / ntp : 1;
+  const int slice = (MAXT == 1) ? tid / ntp : 0;
   int ti[MAXT], tj[MAXT];
   bool act[MAXT];
 #pragma unroll
   for (int m = 0; m < MAXT; ++m) {
-    int idx = tid + m * 256;
-    act[m] = idx < ntp;
+    int idx = (MAXT == 1) ? tid % ntp : tid + m * 256;
+    act[m] = (MAXT == 1) ? (slice < nslices) : (idx < ntp);
     int a = 0, rem = act[m] ? idx : 0;
     // row a of the upper triangle has (nt - a) entries
     while (rem >= nt - a) { rem -= nt - a; ++a; }
@@ -56,23 +60,37 @@ gram_simt_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ Y, 
   const int64_t ntiles = (n + tile_r - 1) / tile_r;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * tile_r;
-    // ---- load tile (coalesced along rows) ----
-    for (int idx = tid; idx < tile_r * q1; idx += 256) {
-      int c = idx / tile_r, r = idx - c * tile_r;
-      int64_t row = row0 + r;
-      T v = T(0);
-      if (row < n) {
-        if (bstride) {   // row-blocked frame: [block][column][FRAME_ROWS]
-          const int64_t o = (row >> 7) * bstride + (row & 127);
-          if (c < p) v = X[o + ((int64_t)c << 7)];
-          else if (c < p + t) v = Y[o + ((int64_t)(c - p) << 7)];
-          else v = mask ? mask[row] : T(1);
-        } else
-        if (c < p) v = X[(int64_t)c * ldx + row];
-        else if (c < p + t) v = Y[(int64_t)(c - p) * ldy + row];
-        else v = mask ? mask[row] : T(1);
+    // ---- load tile (coalesced along rows).  LU independent loads are issued before the first shared-memory store:
+    // with one load in flight per thread this phase was pure latency (~10 us per 128-row tile) ----
+    constexpr int LU = 8;
+    const int total = tile_r * q1;
+    const int tshift = 31 - __clz(tile_r);          // tile_r is a power of two
+    for (int base = tid; base < total; base += 256 * LU) {
+      T v[LU];
+#pragma unroll
+      for (int u = 0; u < LU; ++u) {
+        const int idx = base + u * 256;
+        v[u] = T(0);
+        if (idx < total) {
+          const int c = idx >> tshift, r = idx & (tile_r - 1);
+          const int64_t row = row0 + r;
+          if (row < n) {
+            if (bstride) {   // row-blocked frame: [block][column][FRAME_ROWS]
+              const int64_t o = (row >> 7) * bstride + (row & 127);
+              if (c < p) v[u] = X[o + ((int64_t)c << 7)];
+              else if (c < p + t) v[u] = Y[o + ((int64_t)(c - p) << 7)];
+              else v[u] = mask ? mask[row] : T(1);
+            } else if (c < p) v[u] = X[(int64_t)c * ldx + row];
+            else if (c < p + t) v[u] = Y[(int64_t)(c - p) * ldy + row];
+            else v[u] = mask ? mask[row] : T(1);
+          }
+        }
       }
-      Zs[r * S + c] = v;
+#pragma unroll
+      for (int u = 0; u < LU; ++u) {
+        const int idx = base + u * 256;
+        if (idx < total) Zs[(idx & (tile_r - 1)) * S + (idx >> tshift)] = v[u];
+      }
     }
     if (WEIGHTED) {
       for (int r = tid; r < tile_r; r += 256) ws[r] = (row0 + r < n) ? w[row0 + r] : T(0);
@@ -87,7 +105,7 @@ gram_simt_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ Y, 
       for (int k = 0; k < 16; ++k) loc[k] = T(0);
       const T* pa = Zs + 4 * ti[m];
       const T* pb = Zs + 4 * tj[m];
-      for (int r = 0; r < tile_r; ++r) {
+      for (int r = slice; r < tile_r; r += nslices) {
         Vec4<T> a = *reinterpret_cast<const Vec4<T>*>(pa + r * S);
         Vec4<T> b = *reinterpret_cast<const Vec4<T>*>(pb + r * S);
         if (WEIGHTED) {
@@ -106,7 +124,7 @@ gram_simt_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ Y, 
     __syncthreads();
   }
   // ---- write this CTA's partial (full symmetric) ----
-  double* out = partials + (size_t)blockIdx.x * q1 * q1;
+  double* out = partials + ((size_t)blockIdx.x * nslices + slice) * q1 * q1;
 #pragma unroll
   for (int m = 0; m < MAXT; ++m) {
     if (!act[m]) continue;
@@ -130,13 +148,20 @@ gram_simt_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ Y, 
   }
 }
 
-__global__ void reduce_partials_kernel(const double* __restrict__ partials, int nparts, int len,
-                                       double* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= len) return;
+// one CTA per moment entry: thread k sums parts k, k+128, ... in order, then a fixed-shape tree -> reproducible
+__global__ void __launch_bounds__(128)
+reduce_partials_kernel(const double* __restrict__ partials, int nparts, int len, double* __restrict__ out) {
+  __shared__ double sh[128];
+  const int i = blockIdx.x;
   double s = 0.0;
-  for (int k = 0; k < nparts; ++k) s += partials[(size_t)k * len + i];
-  out[i] = s;
+  for (int k = threadIdx.x; k < nparts; k += 128) s += partials[(size_t)k * len + i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 64; off; off >>= 1) {
+    if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[i] = sh[0];
 }
 
 template <typename T, int MAXT>
@@ -170,10 +195,24 @@ int moments_simt(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, c
   while (tile_r > 16 && (size_t)tile_r * (S + 1) * sizeof(T) > 64 * 1024) tile_r >>= 1;
   size_t smem = (size_t)tile_r * (S + 1) * sizeof(T);
   int64_t ntiles = ceil_div(n > 0 ? n : 1, tile_r);
-  int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count() * 2);
+  // persistent grid: as many CTAs per SM as registers / shared memory allow (load and FMA phases of different CTAs overlap)
+  int per_sm = 2;
+  {
+    int occ = 0;
+    cudaError_t oe = cudaSuccess;
+    if (maxt == 1) {
+      if (w) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gram_simt_kernel<T, 1, true>, 256, smem);
+      else oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gram_simt_kernel<T, 1, false>, 256, smem);
+      if (oe == cudaSuccess && occ >= 1) per_sm = std::min(occ, 4);
+      else (void)cudaGetLastError();
+    }
+  }
+  int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count() * per_sm);
   if (grid < 1) grid = 1;
+  const int nslices = (maxt == 1) ? 256 / ntp : 1;      // must match the kernel's decode
+  const int nparts = grid * nslices;
   double* partials = nullptr;
-  if (dev_alloc((void**)&partials, (size_t)grid * q1 * q1 * sizeof(double), s)) return 1;
+  if (dev_alloc((void**)&partials, (size_t)nparts * q1 * q1 * sizeof(double), s)) return 1;
   int rc;
   switch (maxt) {
     case 1: rc = launch_gram<T, 1>(X, ldx, Y, ldy, w, mask, n, p, t, tile_r, S, grid, smem, partials, bstride, s); break;
@@ -183,7 +222,7 @@ int moments_simt(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, c
   }
   if (rc) { dev_free(partials, s); return rc; }
   int len = q1 * q1;
-  reduce_partials_kernel<<<(len + 255) / 256, 256, 0, s>>>(partials, grid, len, M);
+  reduce_partials_kernel<<<len, 128, 0, s>>>(partials, nparts, len, M);
   cudaError_t e = cudaGetLastError();
   count_launch();
   dev_free(partials, s);
