@@ -164,6 +164,145 @@ reduce_partials_kernel(const double* __restrict__ partials, int nparts, int len,
   if (threadIdx.x == 0) out[i] = sh[0];
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// f64 data: the same moments on the FP64 tensor-core path (mma.sync m8n8k4, SASS DMMA).  Z~ = [X | Y | 1] is cut into
+// NB blocks of 8 columns.  For a 4-row step, lane l holds ONE element per block: Z~[row k0 + l%4][col 8b + l/4] — which
+// is at the same time the A fragment (8 x 4, "row") of block b and the B fragment (4 x 8, "col") of block b, so a step
+// costs NB loads and NB(NB+1)/2 DMMAs per warp, no shared memory and 8x fewer issue slots than the DFMA kernel above.
+// Weights scale the A side only.  Accumulation is f64 throughout; per-CTA partials are combined warp by warp in a
+// fixed order, then across CTAs by reduce_partials_kernel: reproducible.
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int NB>
+__global__ void __launch_bounds__(256)
+gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
+                 const double* __restrict__ w, const double* __restrict__ mask, int64_t n, int p, int t,
+                 double* __restrict__ partials /* [grid][q1*q1] */) {
+  constexpr int NP = NB * (NB + 1) / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);      // [NP][64] CTA-level sum of the warps' accumulators
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, k = lane & 3;
+  const int q1 = p + t + 1;
+  const double* colp[NB];
+  int kind[NB];                                           // 0 data, 1 ones / mask, 2 zero padding
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int c = 8 * b + g;
+    kind[b] = c < p + t ? 0 : (c == p + t ? 1 : 2);
+    colp[b] = c < p ? X + (int64_t)c * ldx : (c < p + t ? Y + (int64_t)(c - p) * ldy : X);
+  }
+  double acc[NP][2];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+
+  const int64_t stride = (int64_t)gridDim.x * 8 * 4;
+  auto load_step = [&](int64_t r0, double* z, double& wv) {
+    const int64_t r = r0 + k;
+    const bool in = r < n;
+    wv = (in && w) ? w[r] : 1.0;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      double v = 0.0;
+      if (in) {
+        if (kind[b] == 0) v = colp[b][r];
+        else if (kind[b] == 1) v = mask ? mask[r] : 1.0;
+      }
+      z[b] = v;
+    }
+  };
+  int64_t r0 = ((int64_t)blockIdx.x * 8 + warp) * 4;
+  double z[NB], zn[NB], wv = 1.0, wn = 1.0;
+  if (r0 < n) load_step(r0, z, wv);
+  for (; r0 < n; r0 += stride) {
+    const bool more = r0 + stride < n;
+    if (more) load_step(r0 + stride, zn, wn);             // next step's loads fly while this step's DMMAs issue
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const double a = z[i] * wv;
+#pragma unroll
+      for (int j = i; j < NB; ++j) { dmma884(acc[idx][0], acc[idx][1], a, z[j]); ++idx; }
+    }
+    if (more) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) z[b] = zn[b];
+      wv = wn;
+    }
+  }
+  // ---- CTA reduction in a fixed order: warp 0 stores, warps 1..7 add one after the other ----
+  for (int wturn = 0; wturn < 8; ++wturn) {
+    if (warp == wturn) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        double* d = sm + i * 64 + g * 8 + 2 * k;
+        if (wturn == 0) { d[0] = acc[i][0]; d[1] = acc[i][1]; }
+        else { d[0] += acc[i][0]; d[1] += acc[i][1]; }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- this CTA's partial, full symmetric q1 x q1 (upper entries of the diagonal blocks are mirrored) ----
+  double* out = partials + (size_t)blockIdx.x * q1 * q1;
+  for (int e = threadIdx.x; e < NP * 64; e += 256) {
+    const int blk = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+    int i = 0, rem = blk;
+    while (rem >= NB - i) { rem -= NB - i; ++i; }
+    const int j = i + rem;
+    const int a = 8 * i + rr, b = 8 * j + cc;
+    if (a < q1 && b < q1 && (i != j || a <= b)) {
+      const double v = sm[e];
+      out[(size_t)a * q1 + b] = v;
+      out[(size_t)b * q1 + a] = v;
+    }
+  }
+}
+
+template <int NB>
+static int launch_dmma(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w, const double* mask,
+                       int64_t n, int p, int t, int grid, double* partials, cudaStream_t s) {
+  const size_t smem = (size_t)(NB * (NB + 1) / 2) * 64 * sizeof(double);
+  gram_dmma_kernel<NB><<<grid, 256, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, partials);
+  PDSB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+// 0 ok, 1 error, -1 not applicable (caller uses the DFMA kernel).  PDSB_K2A_DMMA=0 disables.
+static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w,
+                            const double* mask, int64_t n, int p, int t, double* M, cudaStream_t s) {
+  static const bool enabled = [] { const char* e = getenv("PDSB_K2A_DMMA"); return !(e && e[0] == '0'); }();
+  const int q1 = p + t + 1;
+  const int nb = (q1 + 7) / 8;
+  if (!enabled || nb < 1 || nb > 8 || n < 1) return -1;
+  int grid = (int)std::min<int64_t>(ceil_div(n, 32), (int64_t)sm_count() * 4);
+  if (grid < 1) grid = 1;
+  double* partials = nullptr;
+  if (dev_alloc((void**)&partials, (size_t)grid * q1 * q1 * sizeof(double), s)) return 1;
+  int rc;
+  switch (nb) {
+    case 1: rc = launch_dmma<1>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
+    case 2: rc = launch_dmma<2>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
+    case 3: rc = launch_dmma<3>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
+    case 4: rc = launch_dmma<4>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
+    case 5: rc = launch_dmma<5>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
+    case 6: rc = launch_dmma<6>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
+    case 7: rc = launch_dmma<7>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
+    default: rc = launch_dmma<8>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
+  }
+  if (rc) { dev_free(partials, s); return rc; }
+  const int len = q1 * q1;
+  reduce_partials_kernel<<<len, 128, 0, s>>>(partials, grid, len, M);
+  cudaError_t e = cudaGetLastError();
+  count_launch();
+  dev_free(partials, s);
+  if (e != cudaSuccess) { set_error("reduce_partials launch failed: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
 template <typename T, int MAXT>
 static int launch_gram(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, const T* mask,
                        int64_t n, int p, int t, int tile_r, int S, int grid, size_t smem, double* partials,
@@ -187,6 +326,12 @@ int moments_simt(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, c
                  int p, int t, double* M, cudaStream_t s, int64_t bstride) {
   const int q1 = p + t + 1;
   if (p < 0 || t < 0 || q1 > 260) { set_error("moments: p+t+1=%d out of range (max 260)", q1); return 1; }
+  if constexpr (sizeof(T) == 8) {
+    if (bstride == 0) {      // column-major f64: FP64 tensor-core path for up to 64 columns
+      const int rc = moments_dmma_f64(X, ldx, Y, ldy, w, mask, n, p, t, M, s);
+      if (rc >= 0) return rc;
+    }
+  }
   const int nt = (q1 + 3) / 4, ntp = nt * (nt + 1) / 2;
   const int maxt = (ntp + 255) / 256;
   const int S = nt * 4;  // row stride, multiple of 4 elements
