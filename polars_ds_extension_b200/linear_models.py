@@ -16,7 +16,7 @@ from typing import Any, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from ._lib import MODEL_ELASTIC_NET, MODEL_LR, MODEL_ONLINE_LR, Matrix, PdsbError, lib
+from ._lib import MODEL_ELASTIC_NET, MODEL_LR, MODEL_ONLINE_LR, Matrix, lib
 from .typing import LRSolverMethods, NullPolicy
 
 __all__ = ["LR", "ElasticNet", "OnlineLR"]
