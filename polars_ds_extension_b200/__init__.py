@@ -11,6 +11,8 @@ from .exprs.expr_linear import (  # noqa: F401
     lin_reg,
     lin_reg_report,
     lin_reg_w_rcond,
+    linear_impute,
+    query_ar_coeffs,
     recursive_lin_reg,
     rolling_lin_reg,
     simple_lin_reg,

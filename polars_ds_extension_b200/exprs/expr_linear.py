@@ -18,7 +18,7 @@ from .. import config as cfg
 from ..frame import ColExpr, PluginExpr, col
 from ..typing import LRSolverMethods, NullPolicy
 
-__all__ = ["lin_reg", "simple_lin_reg", "lin_reg_w_rcond", "recursive_lin_reg", "rolling_lin_reg", "lin_reg_report"]
+__all__ = ["lin_reg", "simple_lin_reg", "query_ar_coeffs", "linear_impute", "lin_reg_w_rcond", "recursive_lin_reg", "rolling_lin_reg", "lin_reg_report"]
 
 ExprLike = Union[str, ColExpr]
 
@@ -159,3 +159,47 @@ def lin_reg_report(*x: ExprLike, target: ExprLike, weights: ExprLike | None = No
         symbol = cfg._which_lin_reg("pl_wls_report")
     cols.extend(lr_formula(z) for z in x)
     return PluginExpr(symbol, cols, kwargs, changes_length=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# callers that funnel into lin_reg
+# ---------------------------------------------------------------------------------------------------------------
+def query_ar_coeffs(x: ExprLike, lag: int, add_bias: bool = True, null_policy: NullPolicy = "raise") -> PluginExpr:
+    """Autoregressive coefficients of order `lag` (reference: exprs/ts_features.py:419-461): x_t regressed on
+    x_{t-1} .. x_{t-lag} over rows lag.., bias (if any) last.  One lin_reg call, hence one pass of the moments kernel."""
+    if null_policy not in ("raise", "one", "zero"):
+        try:
+            import math
+
+            if not math.isfinite(float(null_policy)):
+                raise ValueError
+        except Exception:
+            raise ValueError(
+                "`null_polocy` must be 'raise', 'one', 'zero' or any finite numeric string for AR coefficients."
+            )
+    if lag <= 0:
+        raise ValueError("`lag` must be > 0.")
+    xx = lr_formula(x)
+    return lin_reg(*[xx.shift(i).slice(lag).alias(str(i)) for i in range(1, lag + 1)], target=xx.slice(lag),
+                   add_bias=add_bias, null_policy=null_policy)
+
+
+def linear_impute(df, features: List[str], target: str, add_bias: bool = False):
+    """Fill the nulls of `target` with the prediction of a linear regression on `features`, fitted on the rows where
+    everything is present (reference: pipeline/transforms.py:112-155; null_policy="skip", target cast to f64).
+    Returns the frame with the imputed column; rows whose features are null stay null, as `sum_horizontal` of the
+    reference propagates nothing there either (Polars' sum_horizontal skips nulls: those rows get the partial sum)."""
+    import numpy as np
+    import pyarrow as pa
+
+    coeffs = np.asarray(df.select(lin_reg(*features, target=target, add_bias=add_bias, null_policy="skip"))["coeffs"][0].as_py(),
+                        dtype=np.float64)
+    y = df[target].cast(pa.float64()).combine_chunks()
+    missing = ~np.asarray(y.is_valid().to_numpy(zero_copy_only=False), dtype=bool)
+    pred = np.full(len(y), coeffs[-1] if add_bias else 0.0)
+    for f, b in zip(features, coeffs):
+        col_f = df[f].cast(pa.float64()).combine_chunks()
+        ok = np.asarray(col_f.is_valid().to_numpy(zero_copy_only=False), dtype=bool)
+        pred += np.where(ok, col_f.fill_null(0.0).to_numpy(zero_copy_only=False), 0.0) * b   # sum_horizontal ignores nulls
+    vals = np.where(missing, pred, y.fill_null(0.0).to_numpy(zero_copy_only=False))
+    return df.with_columns(**{target: pa.array(vals)})

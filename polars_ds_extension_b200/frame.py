@@ -25,6 +25,8 @@ class ColExpr:
     agg: Optional[str] = None          # "var"
     alias_name: Optional[str] = None
     rechunked: bool = False
+    shift_by: int = 0                  # pl.Expr.shift(n): rows move down by n, nulls enter at the top
+    slice_offset: int = 0              # pl.Expr.slice(offset): drop the first `offset` rows (applied after the shift)
 
     def cast(self, dtype: str) -> "ColExpr":
         return replace(self, cast_to=dtype)
@@ -37,6 +39,12 @@ class ColExpr:
 
     def rechunk(self) -> "ColExpr":
         return replace(self, rechunked=True)
+
+    def shift(self, n: int = 1) -> "ColExpr":
+        return replace(self, shift_by=self.shift_by + int(n))
+
+    def slice(self, offset: int) -> "ColExpr":
+        return replace(self, slice_offset=self.slice_offset + int(offset))
 
     @property
     def out_name(self) -> str:
@@ -74,6 +82,10 @@ class PluginExpr:
                 e = e.var()
             if c.rechunked:
                 e = e.rechunk()
+            if c.shift_by:
+                e = e.shift(c.shift_by)
+            if c.slice_offset:
+                e = e.slice(c.slice_offset)
             if c.alias_name:
                 e = e.alias(c.alias_name)
             return e
@@ -141,6 +153,14 @@ class Frame:
             a = pa.chunked_array([pa.array([v], type=a.type)])
         if c.rechunked:
             a = pa.chunked_array([a.combine_chunks()]) if a.num_chunks != 1 else a
+        if c.shift_by:
+            k = c.shift_by
+            if k < 0:
+                raise ValueError("only forward shifts are needed by the lin_reg callers")
+            k = min(k, len(a))
+            a = pa.chunked_array([pa.nulls(k, type=a.type)] + a.slice(0, len(a) - k).chunks, type=a.type)
+        if c.slice_offset:
+            a = a.slice(min(c.slice_offset, len(a)))
         return a
 
     def evaluate(self, e: PluginExpr) -> pa.Array:
