@@ -58,8 +58,36 @@ class ClockSampler:
         self.index = index
         self.samples = []
         self.proc = None
+        self.nvml = []            # (sm_mhz, reason bitmask) every ~2 ms from NVML, when the library is loadable
+        self.nvml_max = None
+        self._run = False
+
+    def _nvml_loop(self):
+        # in-process NVML polling: nvidia-smi's own loop cannot go below ~100 ms, shorter than one default bench run
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while self._run:
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    bits = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    bits = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.nvml.append((mhz, bits))
+                time.sleep(0.002)
+        except Exception:
+            pass
 
     def start(self):
+        try:
+            self._run = True
+            self.nvml_thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.nvml_thread.start()
+        except Exception:
+            self._run = False
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
@@ -74,6 +102,27 @@ class ClockSampler:
             self.samples.append(line.strip())
 
     def stop(self):
+        self._run = False
+        try:
+            out = self._stop_smi()
+        except Exception as e:      # never let the sampler take the bench line down
+            out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"sampler error: {e}"], "samples": 0}
+        try:
+            nv = list(self.nvml)
+            if len(nv) >= 3:
+                bits = 0
+                for _, b in nv:
+                    bits |= b
+                names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+                reasons = set(out.get("reasons") or []) | {nm for m, nm in names.items() if bits & m}
+                reasons.discard("nvidia-smi unavailable")
+                out = {"sm_mhz": float(np.median([m for m, _ in nv])), "sm_max_mhz": self.nvml_max or out.get("sm_max_mhz"),
+                       "reasons": sorted(reasons), "samples": len(nv), "source": "nvml (2 ms period) + nvidia-smi"}
+        except Exception:
+            pass
+        return out
+
+    def _stop_smi(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
