@@ -115,3 +115,24 @@ def test_python_wrappers_build_reference_kwargs():
         pds.rolling_lin_reg("a", target="y", window_size=1)
     with pytest.raises(ValueError):
         pds.lin_reg("a", target=[])
+
+
+def test_headers_are_plain_c(tmp_path):
+    """include/*.h is the drop-in boundary: it must compile as C99 (no C++-isms), and a C program that links against
+    the shared library must resolve every model / online entry point it declares."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = Path(__file__).resolve().parents[1]
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "pdsb.h"\n#include "polars_plugin_abi.h"\n'
+                   "int main(void) { pdsb_matrix m; pdsb_solve_opts o; (void)m; (void)o; return pdsb_version() < 0; }\n")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{root / 'include'}",
+                    "-fsyntax-only", str(src)], check=True)
+    so = root / "polars_ds_extension_b200" / "_polars_ds_b200.so"
+    exe = tmp_path / "hdr"
+    subprocess.run(["gcc", "-std=c99", f"-I{root / 'include'}", str(src), "-o", str(exe), str(so),
+                    f"-Wl,-rpath,{so.parent}"], check=True)
