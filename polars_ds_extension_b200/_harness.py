@@ -76,8 +76,10 @@ def _chunks(a: ArrayLike) -> List[pa.Array]:
     return [a]
 
 
-def call_plugin(symbol: str, inputs: Sequence[ArrayLike], names: Sequence[str], kwargs: Dict) -> pa.Array:
-    """Call ``_polars_plugin_<symbol>`` like Polars' expression engine does and return the result as a pyarrow array."""
+def call_plugin(symbol: str, inputs: Sequence[ArrayLike], names: Sequence[str], kwargs: Dict,
+                raw_kwargs: bytes | None = None) -> pa.Array:
+    """Call ``_polars_plugin_<symbol>`` like Polars' expression engine does and return the result as a pyarrow array.
+    ``raw_kwargs`` (tests only) replaces the pickled kwargs with arbitrary bytes."""
     L = lib()
     fn = getattr(L, f"_polars_plugin_{symbol}")
     fn.restype = None
@@ -99,8 +101,8 @@ def call_plugin(symbol: str, inputs: Sequence[ArrayLike], names: Sequence[str], 
         exports[i].release = _RELEASE_INPUTS
         exports[i].private_data = 1
         keep.append((sch, arrs, ptrs, chunks))
-    payload = pickle.dumps(dict(kwargs), protocol=5)
-    buf = (C.c_uint8 * len(payload)).from_buffer_copy(payload)
+    payload = pickle.dumps(dict(kwargs), protocol=5) if raw_kwargs is None else bytes(raw_kwargs)
+    buf = (C.c_uint8 * max(len(payload), 1)).from_buffer_copy(payload.ljust(1, b"\0"))
     ret = SeriesExport()
     fn(exports, C.c_size_t(n), buf, C.c_size_t(len(payload)), C.byref(ret), None)
     if not ret.private_data:

@@ -15,6 +15,7 @@
 #include <vector>
 #include <string>
 #include <atomic>
+#include <exception>
 
 using namespace pdsb;
 
@@ -30,7 +31,8 @@ struct PVal {
 bool parse_pickle(const uint8_t* p, size_t n, std::map<std::string, PVal>& out) {
   std::vector<PVal> stack, memo;
   size_t pos = 0;
-  auto need = [&](size_t k) { return pos + k <= n; };
+  auto need = [&](size_t k) { return k <= n - pos; };          // pos <= n always; no overflow for hostile lengths
+  constexpr size_t MAX_MEMO = 1 << 16;                           // a flat kwargs dict memoises a few dozen objects
   auto rd_le = [&](size_t k) { uint64_t v = 0; for (size_t j = 0; j < k; ++j) v |= (uint64_t)p[pos + j] << (8 * j); pos += k; return v; };
   while (pos < n) {
     uint8_t op = p[pos++];
@@ -38,9 +40,9 @@ bool parse_pickle(const uint8_t* p, size_t n, std::map<std::string, PVal>& out) 
       case 0x80: if (!need(1)) return false; pos += 1; break;                  // PROTO
       case 0x95: if (!need(8)) return false; pos += 8; break;                  // FRAME
       case '}': { PVal v; v.kind = PVal::DICT; v.d = std::make_shared<std::map<std::string, PVal>>(); stack.push_back(v); break; }
-      case 0x94: if (stack.empty()) return false; memo.push_back(stack.back()); break;   // MEMOIZE
+      case 0x94: if (stack.empty() || memo.size() >= MAX_MEMO) return false; memo.push_back(stack.back()); break;   // MEMOIZE
       case 'q': if (!need(1) || stack.empty()) return false; { size_t k = p[pos++]; if (memo.size() <= k) memo.resize(k + 1); memo[k] = stack.back(); } break;
-      case 'r': if (!need(4) || stack.empty()) return false; { size_t k = rd_le(4); if (memo.size() <= k) memo.resize(k + 1); memo[k] = stack.back(); } break;
+      case 'r': if (!need(4) || stack.empty()) return false; { size_t k = rd_le(4); if (k >= MAX_MEMO) return false; if (memo.size() <= k) memo.resize(k + 1); memo[k] = stack.back(); } break;
       case '(': { PVal v; v.kind = PVal::MARK; stack.push_back(v); break; }
       case 0x8c: { if (!need(1)) return false; size_t k = p[pos++]; if (!need(k)) return false; PVal v; v.kind = PVal::STR; v.s.assign((const char*)p + pos, k); pos += k; stack.push_back(v); break; }
       case 'X': { if (!need(4)) return false; size_t k = rd_le(4); if (!need(k)) return false; PVal v; v.kind = PVal::STR; v.s.assign((const char*)p + pos, k); pos += k; stack.push_back(v); break; }
@@ -446,7 +448,11 @@ const char* _polars_plugin_get_last_error_message(void) { return get_error(); }
 
 #define DEF_EXPR(name, body, fieldbody)                                                                         \
   void _polars_plugin_##name(SeriesExport* inputs, size_t n_inputs, const uint8_t* kwargs, size_t kwargs_len,   \
-                             SeriesExport* ret, void* ctx) { (void)ctx; body; }                                 \
+                             SeriesExport* ret, void* ctx) {                                                    \
+    (void)ctx;                                                                                                  \
+    try { body; }                                                                                               \
+    catch (const std::exception& e) { set_error("plugin error: %s", e.what()); }   /* never unwind into Polars */ \
+    catch (...) { set_error("plugin error: unknown exception"); } }                                              \
   void _polars_plugin_field_##name(struct ArrowSchema* in_fields, size_t n, struct ArrowSchema* out) {          \
     (void)in_fields; (void)n; fieldbody; }
 

@@ -136,3 +136,41 @@ def test_headers_are_plain_c(tmp_path):
     exe = tmp_path / "hdr"
     subprocess.run(["gcc", "-std=c99", f"-I{root / 'include'}", str(src), "-o", str(exe), str(so),
                     f"-Wl,-rpath,{so.parent}"], check=True)
+
+
+def test_pickle_reader_survives_garbage():
+    """The kwargs bytes come from another process image (Polars): truncated, bit-flipped, foreign-protocol or hostile
+    payloads (huge length fields, huge memo indices) must come back as an error string, never as a crash or an
+    exception unwinding through the C ABI."""
+    import pickle
+    import random
+
+    import pyarrow as pa
+
+    kw = {"bias": True, "null_policy": "skip", "solver": "qr", "l1_reg": 0.0, "l2_reg": 0.1, "tol": 1e-5,
+          "max_iter": 200, "weighted": False, "positive": False, "singular_x_tol": 1e-12}
+    good = pickle.dumps(kw, protocol=5)
+    ins = [pa.array([1.0, 2.0, 3.0]), pa.array([1.0, 2.5, 3.0])]
+    rng = random.Random(0)
+    errors = 0
+
+    def run(b):
+        nonlocal errors
+        try:
+            _harness.call_plugin("pl_lr", ins, ["y", "x"], {}, raw_kwargs=b)
+        except pds.PdsbError:
+            errors += 1
+
+    for k in range(len(good)):
+        run(good[:k])
+    assert errors == len(good)                       # every strict prefix is rejected
+    for _ in range(1500):
+        b = bytearray(good)
+        for _ in range(rng.randint(1, 4)):
+            b[rng.randrange(len(b))] = rng.randrange(256)
+        run(bytes(b))
+    run(b"\\x80\\x05}\\x8d" + (2 ** 63).to_bytes(8, "little") + b"x")           # BINUNICODE8 with an absurd length
+    run(b"\\x80\\x05}\\x8c\\x01ar\\xff\\xff\\xff\\xff.")                          # LONG_BINPUT to memo slot 4e9
+    for proto in (2, 3, 4):
+        run(pickle.dumps(kw, protocol=proto))        # older protocols decode as well (then stop at the device check)
+    assert errors > len(good)
