@@ -54,8 +54,9 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, uuid: str | None = None):
         self.index = index
+        self.uuid = uuid          # "GPU-..." of the CUDA device in use: immune to CUDA_VISIBLE_DEVICES re-numbering
         self.samples = []
         self.proc = None
         self.nvml = []            # (sm_mhz, reason bitmask) every ~2 ms from NVML, when the library is loadable
@@ -68,7 +69,14 @@ class ClockSampler:
             import pynvml
 
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid.encode() if isinstance(self.uuid, str) else self.uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.nvml_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
             while self._run:
                 mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
@@ -283,7 +291,13 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
+    gpu_uuid = None
+    try:
+        u = str(torch.cuda.get_device_properties(device).uuid)
+        gpu_uuid = u if u.startswith("GPU-") else "GPU-" + u
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
     if rank == 0:
         sampler.start()
     launches0 = dev.launch_count()
