@@ -117,7 +117,11 @@ class ClockSampler:
             out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"sampler error: {e}"], "samples": 0}
         try:
             nv = list(self.nvml)
-            if len(nv) >= 3:
+            smi_mhz = out.get("sm_mhz")
+            nv_mhz = float(np.median([m for m, _ in nv])) if nv else None
+            if len(nv) >= 3 and smi_mhz and abs(nv_mhz - smi_mhz) > 0.25 * smi_mhz:
+                out["note"] = f"NVML samples ({nv_mhz:.0f} MHz) disagree with nvidia-smi; nvidia-smi reported"
+            elif len(nv) >= 3:
                 bits = 0
                 for _, b in nv:
                     bits |= b
