@@ -174,3 +174,27 @@ def test_pickle_reader_survives_garbage():
     for proto in (2, 3, 4):
         run(pickle.dumps(kw, protocol=proto))        # older protocols decode as well (then stop at the device check)
     assert errors > len(good)
+
+
+def test_c_client_example_builds_and_fails_loudly_without_gpu(tmp_path):
+    """examples/c_client.c is the smallest non-Python consumer of the host layer; it must compile as C99 against
+    include/pdsb.h, link, and — on a machine without a CUDA device — exit 2 with the library's error string."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    import torch
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = Path(__file__).resolve().parents[1]
+    so = root / "polars_ds_extension_b200" / "_polars_ds_b200.so"
+    exe = tmp_path / "c_client"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{root / 'include'}",
+                    str(root / "examples" / "c_client.c"), str(so), f"-Wl,-rpath,{so.parent}", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stderr + r.stdout
+        assert "coeffs = [2.0" in r.stdout
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
