@@ -352,16 +352,24 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        barrier()
-        e2e = run_e2e(torch, e2e_host, rows, p, args, barrier)
-        if world > 1 and e2e.get("value"):
-            t_e = torch.tensor([e2e["ms_per_step"]], dtype=torch.float64, device=device)
+        def all_ok(flag):
+            torch.cuda.synchronize()
+            if world == 1:
+                return bool(flag)
+            t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return float(t.item()) > 0.5
+
+        e2e = run_e2e(torch, e2e_host, rows, p, args, all_ok)
+        if world > 1:                                   # unconditional on every rank (value None -> contributes 0)
+            t_e = torch.tensor([e2e["ms_per_step"] if e2e.get("value") else 0.0], dtype=torch.float64, device=device)
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-            e2e["ms_per_step"] = float(t_e.item())
-            e2e["value"] = rows * n_gpus / (e2e["ms_per_step"] * 1e-3)
-            e2e["h2d_bytes_per_step"] *= n_gpus
-            e2e["d2h_bytes_per_step"] *= n_gpus
-            e2e["api"] += f"; {n_gpus} ranks concurrently, max over ranks"
+            if e2e.get("value"):
+                e2e["ms_per_step"] = float(t_e.item())
+                e2e["value"] = rows * n_gpus / (e2e["ms_per_step"] * 1e-3)
+                e2e["h2d_bytes_per_step"] *= n_gpus
+                e2e["d2h_bytes_per_step"] *= n_gpus
+                e2e["api"] += f"; {n_gpus} ranks concurrently, max over ranks"
 
     cpu = None
     if rank == 0 and not args.no_cpu and n_gpus == 1:
@@ -409,34 +417,46 @@ def stage_host_copy(torch, X, y, rows, p):
     return host
 
 
-def run_e2e(torch, host, rows, p, args, barrier=None):
-    """Through the plugin C ABI with host buffers: what a Polars user of the drop-in library would time."""
+def run_e2e(torch, host, rows, p, args, all_ok=None):
+    """Through the plugin C ABI with host buffers: what a Polars user of the drop-in library would time.
+    `all_ok(flag) -> bool` is a collective AND over the ranks (and a barrier); every rank calls it exactly twice,
+    whatever happens locally, so a failing rank can never leave the others waiting."""
     import pyarrow as pa
 
     from polars_ds_extension_b200 import _harness
 
-    if isinstance(host, str):
-        return {"value": None, "unit": "rows/s", "error": host}
-    hn = host.numpy()
-    inputs = [pa.array(hn[i]) for i in range(p + 1)]          # zero-copy views of the pinned buffers
-    names = ["y"] + [f"x{i}" for i in range(p)]
-    kw = {"bias": False, "null_policy": "skip", "l1_reg": 0.0, "l2_reg": 0.0, "solver": "qr", "tol": 1e-5,
-          "max_iter": 200, "weighted": False, "positive": False, "singular_x_tol": 1e-6}
-    res = _harness.call_plugin("pl_lr_pred_f32", inputs, names, kw)   # warm-up (pinned result pool, allocator)
-    del res
-    res = _harness.call_plugin("pl_lr_pred_f32", inputs, names, kw)
-    del res
-    torch.cuda.synchronize()
-    if barrier is not None:
-        barrier()
+    all_ok = all_ok or (lambda flag: bool(flag))
+    err = host if isinstance(host, str) else None
+    inputs = names = kw = None
+    if err is None:
+        try:
+            hn = host.numpy()
+            inputs = [pa.array(hn[i]) for i in range(p + 1)]          # zero-copy views of the pinned buffers
+            names = ["y"] + [f"x{i}" for i in range(p)]
+            kw = {"bias": False, "null_policy": "skip", "l1_reg": 0.0, "l2_reg": 0.0, "solver": "qr", "tol": 1e-5,
+                  "max_iter": 200, "weighted": False, "positive": False, "singular_x_tol": 1e-6}
+            for _ in range(2):                                        # warm-up (pinned result pool, allocator)
+                res = _harness.call_plugin("pl_lr_pred_f32", inputs, names, kw)
+                del res
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            err = f"{type(e).__name__}: {e}"
+    if not all_ok(err is None):                                       # collective 1: also the start barrier
+        return {"value": None, "unit": "rows/s", "error": err or "the end-to-end leg failed on another rank"}
     k = max(1, args.e2e_steps)
-    t0 = time.perf_counter()
-    for _ in range(k):
-        res = _harness.call_plugin("pl_lr_pred_f32", inputs, names, kw)
-        assert len(res) == rows
-        del res
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / k
+    dt = None
+    try:
+        t0 = time.perf_counter()
+        for _ in range(k):
+            res = _harness.call_plugin("pl_lr_pred_f32", inputs, names, kw)
+            assert len(res) == rows
+            del res
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / k
+    except Exception as e:  # noqa: BLE001
+        err = f"{type(e).__name__}: {e}"
+    if not all_ok(err is None):                                       # collective 2
+        return {"value": None, "unit": "rows/s", "error": err or "the end-to-end leg failed on another rank"}
     return {"value": rows / dt, "unit": "rows/s", "h2d_bytes_per_step": (p + 1) * rows * 4,
             "d2h_bytes_per_step": 2 * rows * 4, "ms_per_step": dt * 1e3, "steps": k,
             "api": "_polars_plugin_pl_lr_pred_f32 (Arrow C data, pinned host buffers)"}
