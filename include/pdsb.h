@@ -57,6 +57,8 @@ const char* pdsb_last_error(void);
 int pdsb_version(void);
 /* number of this library's kernels launched so far on this process (bench.py's gpu_launches) */
 int64_t pdsb_kernel_launch_count(void);
+/* plugin layer: results exported to the caller whose buffers have not been released yet (ownership tests) */
+int64_t pdsb_plugin_live_results(void);
 /* 1 if the tcgen05/TMA Gram kernel handled the last pdsb_dev_moments_f32 call on this thread, else 0 */
 int pdsb_last_moments_path(void);
 /* force a path for the f32 moments: 0 auto, 1 simt, 2 tcgen05 (tests / ncu) */

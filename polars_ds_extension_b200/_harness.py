@@ -51,22 +51,39 @@ _SCH_REL = C.CFUNCTYPE(None, C.POINTER(ArrowSchema))
 
 
 def _release_inputs_cb(se_ptr):
-    """Release callback the plugin invokes once per input (it owns the inputs)."""
+    """Release callback the plugin invokes once per input (it owns the inputs).
+
+    Same contract as polars-ffi's ``c_release_series_export``: it drops the schema and the *boxes* that held the
+    ArrowArrays, never the arrays themselves — the importer moved those out (``ptr::read``) and releases each through
+    the array's own callback.  A plugin that relies on this callback to release the arrays leaks them; a plugin that
+    does not move them out before calling it reads freed boxes under a real Polars."""
     se = se_ptr.contents
     if not se.private_data:
         return
     if se.field and se.field.contents.release:
         _SCH_REL(se.field.contents.release)(se.field)
-    for i in range(se.len):
-        a = se.arrays[i]
-        if a and a.contents.release:
-            _ARR_REL(a.contents.release)(a)
     se.private_data = None
 
 
 _RELEASE_INPUTS = _RELEASE_T(_release_inputs_cb)
 
 ArrayLike = Union[pa.Array, pa.ChunkedArray]
+
+_PRIM = {b"f": pa.float32(), b"g": pa.float64(), b"l": pa.int64(), b"U": pa.large_string(), b"u": pa.string()}
+
+
+def _type_from_schema(s: ArrowSchema) -> pa.DataType:
+    """Read (not consume) an ArrowSchema the way polars-ffi's import_field_from_c does."""
+    fmt = s.format
+    if fmt in _PRIM:
+        return _PRIM[fmt]
+    kids = [pa.field((s.children[i].contents.name or b"").decode(), _type_from_schema(s.children[i].contents))
+            for i in range(s.n_children)]
+    if fmt == b"+L":
+        return pa.large_list(kids[0])
+    if fmt == b"+s":
+        return pa.struct(kids)
+    raise PdsbError(f"unexpected Arrow format {fmt!r} in a plugin result")
 
 
 def _chunks(a: ArrayLike) -> List[pa.Array]:
@@ -112,9 +129,18 @@ def call_plugin(symbol: str, inputs: Sequence[ArrayLike], names: Sequence[str], 
     try:
         if ret.len != 1:
             raise PdsbError("plugin returned an unexpected number of chunks")
-        out = pa.Array._import_from_c(C.addressof(ret.arrays[0].contents), C.addressof(ret.field.contents))
+        # polars-ffi import_series: `ptr::read` = bitwise copy of the ArrowArray out of its box; the box keeps a stale
+        # `release` pointer, the copy is the owner.  Then the SeriesExport is dropped (its release frees boxes + schema).
+        moved = ArrowArray()
+        C.memmove(C.addressof(moved), C.addressof(ret.arrays[0].contents), C.sizeof(ArrowArray))
+        # the field is only READ (import_field_from_c takes a reference); the export's release drops it
+        out = pa.Array._import_from_c(C.addressof(moved), _type_from_schema(ret.field.contents))
     finally:
         ret.release(C.byref(ret))
+    for sch_i, arrs, _ptrs, _chunks_i in keep:       # the plugin must have moved out (and released) every input chunk
+        for j in range(len(arrs)):
+            if arrs[j].release:
+                raise PdsbError("plugin did not take ownership of an input chunk")
     del keep
     return out
 

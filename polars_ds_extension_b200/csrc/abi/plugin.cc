@@ -16,6 +16,8 @@
 #include <string>
 #include <atomic>
 #include <exception>
+#include <thread>
+#include <algorithm>
 
 using namespace pdsb;
 
@@ -123,12 +125,19 @@ const char* const REQ_MULTI[] = {"bias", "null_policy", "solver", "last_target_i
 const char* const REQ_SWW[] = {"null_policy", "n", "bias", "lambda", "min_size", nullptr};
 
 // ------------------------------------------------------------------ import ---------------------------
+// Ownership follows polars-ffi version_0 (import_series / export_series, crate polars-ffi 0.55.2):
+//   * the callee owns every input SeriesExport.  import_series MOVES each chunk out of its box with ptr::read, keeps it
+//     for as long as the Series lives and releases it through the ArrowArray's own callback; SeriesExport::release only
+//     frees the boxes and the schema and never touches the arrays.  So here: every ArrowArray is moved into `moved`
+//     (source marked released, Arrow-spec move), released by us when the call is over, and then the export is released.
 struct Imported {
   std::vector<pdsb_column> cols;
   std::vector<std::vector<pdsb_chunk>> chunks;
   std::vector<std::string> names;
+  std::vector<ArrowArray> moved;
   SeriesExport* raw = nullptr; size_t n = 0;
-  ~Imported() {   // the callee owns the inputs: release every SeriesExport exactly once
+  ~Imported() {
+    for (ArrowArray& a : moved) if (a.release) a.release(&a);
     for (size_t i = 0; i < n; ++i) if (raw[i].release) raw[i].release(&raw[i]);
   }
 };
@@ -146,6 +155,17 @@ int dtype_from_format(const char* f) {
 bool import_inputs(SeriesExport* in, size_t n, Imported& im) {
   im.raw = in; im.n = n;
   im.cols.resize(n); im.chunks.resize(n); im.names.resize(n);
+  size_t total_chunks = 0;
+  for (size_t i = 0; i < n; ++i) total_chunks += in[i].arrays ? in[i].len : 0;
+  im.moved.reserve(total_chunks);                       // pointers into `moved` stay valid
+  for (size_t i = 0; i < n; ++i)
+    for (size_t c = 0; in[i].arrays && c < in[i].len; ++c) {
+      ArrowArray* src = in[i].arrays[c];
+      if (!src) continue;
+      im.moved.push_back(*src);
+      src->release = nullptr;
+    }
+  size_t mv = 0;
   for (size_t i = 0; i < n; ++i) {
     SeriesExport& se = in[i];
     if (!se.field) { set_error("plugin input %zu has no schema", i); return false; }
@@ -154,7 +174,8 @@ bool import_inputs(SeriesExport* in, size_t n, Imported& im) {
     im.names[i] = se.field->name ? se.field->name : "";
     int64_t nulls = 0;
     for (size_t c = 0; c < se.len; ++c) {
-      ArrowArray* a = se.arrays[c];
+      if (!se.arrays || !se.arrays[c]) { set_error("plugin input %zu has a null chunk", i); return false; }
+      ArrowArray* a = &im.moved[mv++];
       pdsb_chunk ch;
       ch.validity = (a->n_buffers > 0 && a->null_count != 0) ? (const uint8_t*)a->buffers[0] : nullptr;
       ch.data = a->n_buffers > 1 ? a->buffers[1] : nullptr;
@@ -170,7 +191,12 @@ bool import_inputs(SeriesExport* in, size_t n, Imported& im) {
 }
 
 // ------------------------------------------------------------------ export ---------------------------
-struct SharedResult { pdsb_host_result r; std::atomic<int> refs{1}; };
+std::atomic<int64_t> g_live_results{0};   // exported results whose buffers have not been released yet (tests)
+struct SharedResult {
+  pdsb_host_result r; std::atomic<int> refs{1};
+  SharedResult() { memset(&r, 0, sizeof(r)); g_live_results.fetch_add(1); }
+  ~SharedResult() { g_live_results.fetch_sub(1); }
+};
 void sr_unref(SharedResult* s) { if (s && s->refs.fetch_sub(1) == 1) { pdsb_host_result_free(&s->r); delete s; } }
 
 struct Node {
@@ -222,12 +248,16 @@ void fill_array(Node& nd, ArrowArray* a, SharedResult* sr) {
   a->release = release_array; a->private_data = p;
 }
 
+// Output: the importer (polars-ffi import_series) takes the ArrowArray by ptr::read — a bitwise copy that leaves
+// `release` set in our box — and owns it from then on; it drops the SeriesExport right after, whose release callback
+// (c_release_series_export in polars-ffi) frees the boxes and the schema only.  Calling the array's release here would
+// free the buffers under the imported Series and be followed by a second release when that Series is dropped.
 struct SePriv { ArrowSchema* field; ArrowArray** arrays; };
 void release_series(SeriesExport* se) {
   if (!se || !se->private_data) return;
   SePriv* p = (SePriv*)se->private_data;
   if (p->field) { if (p->field->release) p->field->release(p->field); free(p->field); }
-  if (p->arrays) { if (p->arrays[0]) { if (p->arrays[0]->release) p->arrays[0]->release(p->arrays[0]); free(p->arrays[0]); } free(p->arrays); }
+  if (p->arrays) { free(p->arrays[0]); free(p->arrays); }
   delete p;
   se->private_data = nullptr; se->release = nullptr; se->field = nullptr; se->arrays = nullptr; se->len = 0;
 }
@@ -243,11 +273,38 @@ void export_series(Node& root, SharedResult* sr, SeriesExport* ret) {
 }
 
 // ---- node builders ----
+// one byte per row (0/1) -> Arrow validity bitmap.  8 rows per step (multiply-gather of the low bits), row ranges
+// spread over a few threads for long outputs (rolling / recursive: one validity entry per input row).
+void bitmap_range(const uint8_t* valid, int64_t b0, int64_t b1 /* byte range of the bitmap */, int64_t n, uint8_t* bm, int64_t* ones) {
+  int64_t cnt = 0;
+  for (int64_t b = b0; b < b1; ++b) {
+    const int64_t i = b << 3;
+    uint8_t v = 0;
+    if (i + 8 <= n) {
+      uint64_t x; memcpy(&x, valid + i, 8);
+      x = (x | (x >> 1) | (x >> 2) | (x >> 3) | (x >> 4) | (x >> 5) | (x >> 6) | (x >> 7)) & 0x0101010101010101ull;   // any non-zero byte -> 1
+      v = (uint8_t)((x * 0x0102040810204080ull) >> 56);
+    } else {
+      for (int64_t k = i; k < n; ++k) if (valid[k]) v |= (uint8_t)(1u << (k & 7));
+    }
+    bm[b] = v;
+    cnt += __builtin_popcount(v);
+  }
+  *ones = cnt;
+}
 uint8_t* bitmap_from_bytes(const uint8_t* valid, int64_t n, int64_t* null_count) {
-  uint8_t* bm = (uint8_t*)calloc((size_t)((n + 7) / 8 + 8), 1);
-  int64_t nulls = 0;
-  for (int64_t i = 0; i < n; ++i) { if (valid[i]) bm[i >> 3] |= (uint8_t)(1u << (i & 7)); else ++nulls; }
-  *null_count = nulls;
+  const int64_t nb = (n + 7) / 8;
+  uint8_t* bm = (uint8_t*)calloc((size_t)(nb + 8), 1);
+  const int nt = n >= (int64_t(1) << 22) ? (int)std::min<int64_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  std::vector<int64_t> ones(nt, 0);
+  if (nt == 1) bitmap_range(valid, 0, nb, n, bm, &ones[0]);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(bitmap_range, valid, nb * t / nt, nb * (t + 1) / nt, n, bm, &ones[t]);
+    for (auto& t : th) t.join();
+  }
+  int64_t tot = 0; for (int64_t o : ones) tot += o;
+  *null_count = n - tot;
   return bm;
 }
 uint8_t* bitmap_const(int64_t n, bool v) {
@@ -422,9 +479,9 @@ void run_online(SeriesExport* in, size_t n, const uint8_t* kwp, size_t kwn, Seri
 
 void run_by(SeriesExport* in, size_t n, const uint8_t* kwp, size_t kwn, SeriesExport* ret, bool f32) {
   fail(ret);
-  if (n < 3) { set_error("pl_lr_by: need offsets, target and at least one feature"); for (size_t i = 0; i < n; ++i) if (in[i].release) in[i].release(&in[i]); return; }
   Imported im;
   if (!import_inputs(in, n, im)) return;
+  if (n < 3) { set_error("pl_lr_by: need offsets, target and at least one feature"); return; }
   Kwargs kw;
   if (!load_kwargs(kwp, kwn, kw, REQ_LR)) return;
   const pdsb_column& oc = im.cols[0];
@@ -444,6 +501,7 @@ void run_by(SeriesExport* in, size_t n, const uint8_t* kwp, size_t kwn, SeriesEx
 extern "C" {
 
 uint32_t _polars_plugin_get_version(void) { return (0u << 16) | 1u; }
+int64_t pdsb_plugin_live_results(void) { return g_live_results.load(); }
 const char* _polars_plugin_get_last_error_message(void) { return get_error(); }
 
 #define DEF_EXPR(name, body, fieldbody)                                                                         \

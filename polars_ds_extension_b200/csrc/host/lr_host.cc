@@ -470,6 +470,13 @@ int host_grouped_t(const pdsb_column* cols, int n_cols, const int64_t* offsets, 
   NullPolicy nanpol{NullKind::IGNORE, 0.0};
   if (build_frame<T>(cols, n_cols, 1, nullptr, nanpol, false, true, F, bag, s)) return 1;
   if (n_groups < 1 || offsets[0] != 0 || offsets[n_groups] != F.n) { set_error("grouped lin_reg: bad group offsets"); return 1; }
+  // the offsets are user data (an Int64 column): every group must be a row range inside the frame, or the kernel
+  // would read outside X / y
+  for (int64_t g = 0; g < n_groups; ++g)
+    if (offsets[g] < 0 || offsets[g] > offsets[g + 1] || offsets[g + 1] > F.n) {
+      set_error("grouped lin_reg: group offsets must be non-decreasing and within [0, n] (group %lld)", (long long)g);
+      return 1;
+    }
   const int add_bias = kw->bias ? 1 : 0;
   const int q = F.p + add_bias;
   pdsb_solve_opts o{};

@@ -15,6 +15,7 @@
 #include "../common.h"
 #include "../kernels/kernels.h"
 #include "host.h"
+#include <mutex>
 
 namespace pdsb {
 namespace {
@@ -89,6 +90,10 @@ struct pdsb_online_lr {
   double* w;     // [q]  (bias last)
   double* x;     // [q]  staging for one row
   bool fit;
+  // the handle owns its stream and a lock: update / get / set from ANY thread are ordered on this one stream and never
+  // race on inv / w / the single staging row (the Python OnlineLR object carries no thread affinity)
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
 };
 
 extern "C" {
@@ -171,11 +176,18 @@ pdsb_online_lr* pdsb_online_lr_new(int n_coef, int has_bias) {
     return nullptr;
   }
   h->inv = blk; h->w = blk + (size_t)n_coef * n_coef; h->x = h->w + n_coef;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("pdsb_online_lr_new: stream creation failed");
+    cudaFree(blk);
+    delete h;
+    return nullptr;
+  }
   return h;
 }
 
 void pdsb_online_lr_free(pdsb_online_lr* h) {
   if (!h) return;
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   cudaFree(h->inv);
   delete h;
 }
@@ -183,8 +195,8 @@ void pdsb_online_lr_free(pdsb_online_lr* h) {
 /* coeffs: n_coef values (bias last), inv: n_coef^2 row-major  (OnlineLR::set_coeffs_bias_inverse, :29-52) */
 int pdsb_online_lr_set(pdsb_online_lr* h, const double* coeffs, const double* inv) {
   if (!h || !coeffs || !inv) { set_error("pdsb_online_lr_set: null argument"); return 1; }
-  cudaStream_t s, s2;
-  if (thread_streams(&s, &s2)) return 1;
+  std::lock_guard<std::mutex> lk(h->mu);
+  cudaStream_t s = h->stream;
   PDSB_CUDA_OK(cudaMemcpyAsync(h->w, coeffs, (size_t)h->q * sizeof(double), cudaMemcpyHostToDevice, s));
   PDSB_CUDA_OK(cudaMemcpyAsync(h->inv, inv, (size_t)h->q * h->q * sizeof(double), cudaMemcpyHostToDevice, s));
   PDSB_CUDA_OK(cudaStreamSynchronize(s));
@@ -196,19 +208,19 @@ int pdsb_online_lr_set(pdsb_online_lr* h, const double* coeffs, const double* in
 int pdsb_online_lr_update(pdsb_online_lr* h, const double* x_row, double y, double c) {
   if (!h || !x_row) { set_error("pdsb_online_lr_update: null argument"); return 1; }
   if (!h->fit) { set_error("Matrix is not learned yet."); return 1; }
-  cudaStream_t s, s2;
-  if (thread_streams(&s, &s2)) return 1;
+  std::lock_guard<std::mutex> lk(h->mu);
+  cudaStream_t s = h->stream;
   const int pf = h->q - h->has_bias;
   if (pf > 0) PDSB_CUDA_OK(cudaMemcpyAsync(h->x, x_row, (size_t)pf * sizeof(double), cudaMemcpyHostToDevice, s));
   if (woodbury_update(h->inv, h->w, h->q, h->has_bias, h->x, y, c, s)) return 1;
-  return 0;   // stream-ordered: the next update / get on this thread sees the new state
+  return 0;   // stream-ordered on the handle's stream: the next update / get (from any thread) sees the new state
 }
 
 int pdsb_online_lr_get(pdsb_online_lr* h, double* coeffs, double* inv) {
   if (!h) { set_error("pdsb_online_lr_get: null handle"); return 1; }
   if (!h->fit) { set_error("Matrix is not learned yet."); return 1; }
-  cudaStream_t s, s2;
-  if (thread_streams(&s, &s2)) return 1;
+  std::lock_guard<std::mutex> lk(h->mu);
+  cudaStream_t s = h->stream;
   if (coeffs) PDSB_CUDA_OK(cudaMemcpyAsync(coeffs, h->w, (size_t)h->q * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (inv) PDSB_CUDA_OK(cudaMemcpyAsync(inv, h->inv, (size_t)h->q * h->q * sizeof(double), cudaMemcpyDeviceToHost, s));
   PDSB_CUDA_OK(cudaStreamSynchronize(s));

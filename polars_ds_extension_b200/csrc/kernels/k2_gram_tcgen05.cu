@@ -594,7 +594,7 @@ gram_tcgen05_rawhi_kernel(const __grid_constant__ CUtensorMap tmap, const float*
 //              column sums from the ones row.   sum(y), sum(y^2) and the row count never touch the tensor core: the
 //              lane that builds lo(y) accumulates them (fp32 per box, f64 across boxes).
 // Same ring / barrier protocol as the raw-hi kernel.
-struct YSide { double sy, syy, cnt; };
+constexpr int YSIDE_STRIDE = 32;   // doubles per (CTA, converter set): [3u+0] sum y_u, [3u+1] sum y_u^2, [2] count, [12 + 4j + k] y_j.y_k
 
 template <int NB, int NCONV>
 __global__ void __launch_bounds__((2 + 4 * NCONV + 4 * EPI_SETS) * 32, 1)
@@ -711,8 +711,8 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
       const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
       const int xrow = zx + m;
       const uint32_t sw = (uint32_t)(xrow & 7);
-      float sy = 0.0f, syy = 0.0f;
-      double dsy = 0.0, dsyy = 0.0, dcnt = 0.0;
+      float sy = 0.0f, syy = 0.0f, sxy[3] = {0.0f, 0.0f, 0.0f};   // sxy[d-1]: y_j . y_{j+d} (multi-target cross moments)
+      double dsy = 0.0, dsyy = 0.0, dcnt = 0.0, dxy[3] = {0.0, 0.0, 0.0};
       for (uint32_t it = set; it < my_stages; it += NCONV) {
         const uint32_t rs = it % RING, rph = (it / RING) & 1;
         const uint32_t s = it % XAB, sph = (it / XAB) & 1;
@@ -753,6 +753,14 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
               *reinterpret_cast<uint4*>(tile + (size_t)lr * 128 + ((c ^ (lr & 7)) << 4)) = lo;
               sy += (y0 + y1) + (y2 + y3);
               syy = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, syy))));
+#pragma unroll
+              for (int d = 1; d < 4; ++d)
+                if (j + d < t) {
+                  const int kr = zy + j + d;
+                  const uint4 kv = *reinterpret_cast<const uint4*>(tile + (size_t)kr * 128 + ((c ^ (kr & 7)) << 4));
+                  sxy[d - 1] = fmaf(y0, __uint_as_float(kv.x), fmaf(y1, __uint_as_float(kv.y),
+                               fmaf(y2, __uint_as_float(kv.z), fmaf(y3, __uint_as_float(kv.w), sxy[d - 1]))));
+                }
             }
             if (!fast) {
               // masked / ragged stage: lanes 0..7 rewrite the ones row with the 32 mask values of this box
@@ -780,6 +788,8 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
           tmem_st32(tmem + lane_addr + (uint32_t)(XA_COL0 + s * A_SLOT_COLS + b * BOX_ROWS), v);
         }
         dsy += (double)sy; dsyy += (double)syy; sy = 0.0f; syy = 0.0f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { dxy[d] += (double)sxy[d]; sxy[d] = 0.0f; }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         if (quad == 0) fence_async_smem();    // lo(y) / ones rows written through the generic proxy
         tc_fence_before();
@@ -788,13 +798,19 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
       }
       if (quad == 0) {
         // reduce the 8 chunk-lanes of every target (fixed order -> reproducible) and the masked-row count
-        double* ys = yside + ((size_t)blockIdx.x * NCONV + set) * 12;
+        double* ys = yside + ((size_t)blockIdx.x * NCONV + set) * YSIDE_STRIDE;
         for (int off = 4; off; off >>= 1) {
           dsy += __shfl_down_sync(0xffffffffu, dsy, off, 8);
           dsyy += __shfl_down_sync(0xffffffffu, dsyy, off, 8);
           dcnt += __shfl_down_sync(0xffffffffu, dcnt, off, 8);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) dxy[d] += __shfl_down_sync(0xffffffffu, dxy[d], off, 8);
         }
-        if ((lane & 7) == 0 && (lane >> 3) < t) { ys[(lane >> 3) * 3 + 0] = dsy; ys[(lane >> 3) * 3 + 1] = dsyy; }
+        if ((lane & 7) == 0 && (lane >> 3) < t) {
+          const int j = lane >> 3;
+          ys[j * 3 + 0] = dsy; ys[j * 3 + 1] = dsyy;
+          for (int d = 1; d < 4; ++d) if (j + d < t) ys[12 + j * 4 + (j + d)] = dxy[d - 1];
+        }
         if (lane == 0) ys[2] = dcnt;
       }
     }
@@ -865,15 +881,17 @@ __global__ void gram_finalize_xonly_kernel(const double* __restrict__ partials, 
     r = sum_d(hi_lane(i), q + t) + sum_d(hi_lane(i) + 32, q + t);
   } else {
     // y / ones block from the side accumulators
-    double sy[4] = {0, 0, 0, 0}, syy[4] = {0, 0, 0, 0}, cnt = 0.0;
+    double sy[4] = {0, 0, 0, 0}, syy[4] = {0, 0, 0, 0}, cnt = 0.0, cross = 0.0;
+    const bool want_cross = (j < p + t) && (i != j);
     for (int k = 0; k < nparts * nconv; ++k) {
-      const double* ys = yside + (size_t)k * 12;
+      const double* ys = yside + (size_t)k * YSIDE_STRIDE;
       for (int u = 0; u < t; ++u) { sy[u] += ys[u * 3 + 0]; syy[u] += ys[u * 3 + 1]; }
       cnt += ys[2];
+      if (want_cross) cross += ys[12 + (i - p) * 4 + (j - p)];
     }
     const double count = masked ? cnt : (double)n;
     if (j == p + t) r = (i == p + t) ? count : sy[i - p];
-    else r = (i == j) ? syy[i - p] : nan("");      // y_i . y_j for i != j is not produced (no consumer needs it)
+    else r = (i == j) ? syy[i - p] : cross;         // y_i . y_j from the side lanes (exact products, f64 across stages)
   }
   M[(size_t)i * q1 + j] = r;
   M[(size_t)j * q1 + i] = r;
@@ -1031,6 +1049,7 @@ int xonly_nconv() {
 bool moments_tcgen05_supported(const float* X, int64_t ldx, const float* Y, int64_t ldy, int64_t n, int p, int t) {
   if (getenv("PDSB_DISABLE_TCGEN05")) return false;
   if (n < 4096) return false;                 // latency-bound sizes stay on the SIMT kernel
+  if (n >= (int64_t(1) << 31) - STAGE_ROWS) return false;   // the 2-D tensor map is addressed with int32 row coordinates
   if (!get_encode_fn()) return false;
   return analyse(X, ldx, Y, ldy, p, t).ok;
 }
@@ -1094,7 +1113,7 @@ static int moments_tcgen05_core(const Geometry& g, int64_t ldx, const float* mas
   int grid = sm_count();
   if (stages_total < grid) grid = (int)stages_total;
   double* partials = nullptr;
-  if (dev_alloc((void**)&partials, ((size_t)grid * 128 * N + (size_t)grid * 3 * 12) * sizeof(double), s)) return 1;
+  if (dev_alloc((void**)&partials, ((size_t)grid * 128 * N + (size_t)grid * 3 * YSIDE_STRIDE) * sizeof(double), s)) return 1;
   double* yside = partials + (size_t)grid * 128 * N;
   int rc;
   const int q1 = p + t + 1;

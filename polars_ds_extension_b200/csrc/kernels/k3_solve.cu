@@ -165,10 +165,10 @@ __device__ void jacobi_eigen(double* A, double* V, int q, double* cs) {
     if (tid == 0) sh_rot = 0;
     __syncthreads();
     for (int r = 0; r < m; ++r) {
-      if (tid < npairs) {
+      for (int pi = tid; pi < npairs; pi += NT) {     // any q: pairs strided over the CTA
         int a, b;
-        if (tid == 0) { a = m; b = r; }
-        else { a = (r + tid) % m; b = (r - tid + m) % m; }
+        if (pi == 0) { a = m; b = r; }
+        else { a = (r + pi) % m; b = (r - pi % m + m) % m; }
         if (a > b) { int x = a; a = b; b = x; }
         double c = 1.0, s = 0.0;
         if (b < q && a != b) {
@@ -185,8 +185,8 @@ __device__ void jacobi_eigen(double* A, double* V, int q, double* cs) {
             if (s != 0.0) sh_rot = 1;
           }
         } else { a = -1; }
-        cs[4 * tid + 0] = c; cs[4 * tid + 1] = s;
-        cs[4 * tid + 2] = (double)a; cs[4 * tid + 3] = (double)b;
+        cs[4 * pi + 0] = c; cs[4 * pi + 1] = s;
+        cs[4 * pi + 2] = (double)a; cs[4 * pi + 3] = (double)b;
       }
       __syncthreads();
       // column update A <- A J, V <- V J
@@ -259,11 +259,19 @@ __global__ void __launch_bounds__(NT) solve_kernel(SolveParams P) {
     const bool gated = (o.method == PDSB_METHOD_LSTSQ) && o.singular_x_tol > 0.0;
     if (gated && tid == 0) {
       double s = 0.0; int bad = 0;
-      for (int i = 0; i < q; ++i) { double d = at(G, q, i, i); if (!(d > 0.0)) bad = 1; else s += log(d); }
+      // faer_solve_lr_gated (lr_solvers.rs:341-347): `d <= 0` gates; a NaN diagonal (null_policy "ignore" with NaN data)
+      // compares false, poisons ln_den, and every later `<= ln_tol` test is false too: the reference SOLVES and returns
+      // NaN coefficients (QR / LLT); its SVD fails to converge on NaN and gates (:360).
+      for (int i = 0; i < q; ++i) { double d = at(G, q, i, i); if (d <= 0.0) bad = 1; else s += log(d); }
       sh_lnden = s; if (bad) sh_gate = 1;
     }
     __syncthreads();
     if (sh_gate) { if (tid == 0) *P.status = PDSB_GATED; return; }
+    if (gated && isnan(sh_lnden)) {
+      if (o.solver == PDSB_SOLVER_SVD) { if (tid == 0) *P.status = PDSB_GATED; return; }
+      for (int idx = tid; idx < q * t; idx += NT) P.beta[idx] = nan("");
+      return;
+    }
     const double ln_tol = gated ? log(o.singular_x_tol) : 0.0;
     int solver = o.solver;
     if (o.method == PDSB_METHOD_INV) solver = PDSB_SOLVER_QR;
@@ -315,7 +323,7 @@ __global__ void __launch_bounds__(NT) solve_kernel(SolveParams P) {
     if (gated) {
       if (tid == 0) { double s = 0.0; for (int i = 0; i < q; ++i) s += log(fabs(at(A, q, i, i))); sh_lndet = s; }
       __syncthreads();
-      if (sh_lndet - sh_lnden <= ln_tol || isnan(sh_lndet)) { if (tid == 0) *P.status = PDSB_GATED; return; }
+      if (sh_lndet - sh_lnden <= ln_tol) { if (tid == 0) *P.status = PDSB_GATED; return; }
     }
     qr_backsolve(A, q, B, nrhs, perm, V /* reuse V as X (q x nrhs) */);
     for (int idx = tid; idx < q * t; idx += NT) P.beta[idx] = V[idx];

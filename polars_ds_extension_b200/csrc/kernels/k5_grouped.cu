@@ -210,9 +210,11 @@ __global__ void __launch_bounds__(128) group_solve_kernel(GroupSolveArgs a) {
   if (gated) {
     for (int i = 0; i < q; ++i) {
       double d = AA(i, i);
-      if (!(d > 0.0)) { a.status[g] = PDSB_GATED; for (int k = 0; k < q; ++k) out[k] = nan(""); return; }
+      if (d <= 0.0) { a.status[g] = PDSB_GATED; for (int k = 0; k < q; ++k) out[k] = nan(""); return; }
       ln_den += log(d);
     }
+    // NaN diagonal: the reference's comparisons are all false -> it solves and returns NaN coefficients (k3_solve.cu)
+    if (isnan(ln_den)) { a.status[g] = PDSB_OK; for (int k = 0; k < q; ++k) out[k] = nan(""); return; }
   }
   const double ln_tol = gated ? log(a.tol) : 0.0;
   int perm[64];
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(128) group_solve_kernel(GroupSolveArgs a) {
       AA(k, k) = alpha;
       ln_det += log(fabs(alpha));
     }
-    if (gated && (ln_det - ln_den <= ln_tol || isnan(ln_det))) {
+    if (gated && ln_det - ln_den <= ln_tol) {
       a.status[g] = PDSB_GATED; for (int k = 0; k < q; ++k) out[k] = nan(""); return;
     }
     for (int i = q - 1; i >= 0; --i) {

@@ -169,8 +169,17 @@ def test_pickle_reader_survives_garbage():
         for _ in range(rng.randint(1, 4)):
             b[rng.randrange(len(b))] = rng.randrange(256)
         run(bytes(b))
-    run(b"\\x80\\x05}\\x8d" + (2 ** 63).to_bytes(8, "little") + b"x")           # BINUNICODE8 with an absurd length
-    run(b"\\x80\\x05}\\x8c\\x01ar\\xff\\xff\\xff\\xff.")                          # LONG_BINPUT to memo slot 4e9
+    hostile = [
+        b"\x80\x05}\x8d" + (2 ** 63).to_bytes(8, "little") + b"x",          # BINUNICODE8 with an absurd length
+        b"\x80\x05}\x8c\x01ar\xff\xff\xff\xff.",                          # LONG_BINPUT to memo slot 4e9
+        b"\x80\x05}X\xff\xff\xff\x7fabc.",                                 # BINUNICODE longer than the payload
+        b"\x80\x05}j\xff\xff\xff\x7f.",                                    # LONG_BINGET of a slot that does not exist
+    ]
+    assert hostile[0][0] == 0x80 and hostile[0][3] == 0x8d                  # real opcodes, not ASCII backslashes
+    before = errors
+    for h in hostile:
+        run(h)
+    assert errors == before + len(hostile)
     for proto in (2, 3, 4):
         run(pickle.dumps(kw, protocol=proto))        # older protocols decode as well (then stop at the device check)
     assert errors > len(good)
@@ -198,3 +207,37 @@ def test_c_client_example_builds_and_fails_loudly_without_gpu(tmp_path):
         assert "coeffs = [2.0" in r.stdout
     else:
         assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def test_inputs_are_moved_and_released_like_polars_ffi():
+    """polars-ffi's import_series moves every chunk out of its box (ptr::read) and releases it through the ArrowArray's
+    own callback; SeriesExport::release only drops the boxes and the schema.  The harness mimics that, so a plugin that
+    left the arrays to the export's release callback would leak them: the numpy buffers behind the inputs must be
+    unreferenced again after the call — also on the error path (this runs without a GPU too)."""
+    import gc
+    import sys
+
+    import pyarrow as pa
+
+    y = np.arange(1000.0)
+    x = np.arange(1000.0) * 0.5
+    base = (sys.getrefcount(y), sys.getrefcount(x))
+    ins = [pa.chunked_array([pa.array(y[:400]), pa.array(y[400:])]), pa.array(x)]
+    kw = {"bias": False, "null_policy": "raise", "solver": "qr", "l1_reg": 0.0, "l2_reg": 0.0, "tol": 0.0}
+    held = (sys.getrefcount(y), sys.getrefcount(x))
+    assert held[0] > base[0] and held[1] > base[1]
+    try:
+        out = _harness.call_plugin("pl_lr", ins, ["y", "x"], kw)
+        del out
+    except pds.PdsbError:
+        pass
+    try:
+        _harness.call_plugin("pl_lr", ins, ["y", "x"], {"bias": True})      # kwargs error path
+    except pds.PdsbError:
+        pass
+    del ins
+    gc.collect()
+    assert (sys.getrefcount(y), sys.getrefcount(x)) == base
+    L = lib()
+    L.pdsb_plugin_live_results.restype = C.c_int64
+    assert L.pdsb_plugin_live_results() == 0
