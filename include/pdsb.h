@@ -65,6 +65,32 @@ int pdsb_last_moments_path(void);
 void pdsb_set_moments_path(int path);
 /* make `device` current for the calling thread inside the library's (statically linked) CUDA runtime */
 int pdsb_set_device(int device);
+/* ---- multi-GPU.  Rows shard naturally: every GPU builds the moments of its row range, ONE
+ * ncclAllReduce(sum, f64) of (p+t+1)^2 values over NVLink joins them, every GPU solves redundantly and predicts its
+ * own rows.  The Gram being sharded: get_xtx_with_lambda / build_xty (src/linear/lr/lr_solvers.rs:183-211, 262-278).
+ * NCCL is bound at run time (dlopen of libnccl.so.2; PDS_B200_NCCL_LIB overrides the name).
+ *
+ * (i) device group, single process (a Polars process): the host layer splits every large pdsb_host_lin_reg call
+ *     (>= PDS_B200_SHARD_MIN_ROWS rows, default 2^21) into one contiguous row shard per device; each shard is uploaded
+ *     over its own PCIe link by its own worker thread.  Chosen by the environment variable PDS_B200_DEVICES
+ *     ("8" = first 8, "all", or "0,2,5") or by pdsb_set_devices (n <= 1 returns to single-device operation). */
+int pdsb_set_devices(const int* devices, int n);
+int pdsb_device_group_size(void);
+/* (ii) world communicator, one process per GPU (torchrun / Dask / Ray workers): rank 0 creates a 128-byte id, the
+ *     launcher distributes it, every rank joins.  From then on every pdsb_host_lin_reg / plugin lin_reg call is
+ *     COLLECTIVE: each rank passes its own rows and all ranks get the coefficients of the fit over the union (and the
+ *     predictions of their own rows).  pdsb_comm_destroy leaves the communicator. */
+int pdsb_comm_unique_id(void* out128);
+int pdsb_comm_init_rank(int world_size, int rank, const void* id128);
+void pdsb_comm_destroy(void);
+int pdsb_comm_size(void);
+int pdsb_nccl_version(void); /* 0 when NCCL could not be loaded */
+/* device layer of (ii): in-place sum of `count` f64 values over the world communicator, enqueued on `stream`
+ * (no-op without a communicator).  This is the one exchange of the row-sharded path: count = (p+t+1)^2. */
+int pdsb_dev_allreduce_f64(double* buf, int64_t count, void* stream);
+/* bytes of the calling thread's last host-layer upload that went through the pinned staging ring (pageable input) */
+int64_t pdsb_last_staged_bytes(void);
+
 /* tcgen05 kernel variant: 1 raw-hi (default; B operand = raw TMA tile, hardware truncation), 0 explicit-hi cross-check */
 void pdsb_set_tc_variant(int v);
 

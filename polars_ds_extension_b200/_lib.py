@@ -84,6 +84,13 @@ def lib() -> C.CDLL:
     L.pdsb_online_lr_set.argtypes = [vp, vp, vp]
     L.pdsb_online_lr_update.argtypes = [vp, vp, dbl, dbl]
     L.pdsb_online_lr_get.argtypes = [vp, vp, vp]
+    L.pdsb_set_devices.argtypes = [C.POINTER(ci), ci]
+    L.pdsb_comm_unique_id.argtypes = [vp]
+    L.pdsb_comm_init_rank.argtypes = [ci, ci, vp]
+    L.pdsb_comm_destroy.restype = None
+    L.pdsb_dev_allreduce_f64.argtypes = [vp, i64, vp]
+    L.pdsb_last_staged_bytes.restype = i64
+    L.pdsb_plugin_live_results.restype = i64
     _lib = L
     return L
 

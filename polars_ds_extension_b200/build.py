@@ -31,6 +31,8 @@ SOURCES = [
     "kernels/k10_models.cu",
     "host/context.cc",
     "host/api_dev.cc",
+    "host/h2d.cc",
+    "host/multi_gpu.cc",
     "host/lr_host.cc",
     "host/models_host.cc",
     "abi/plugin.cc",

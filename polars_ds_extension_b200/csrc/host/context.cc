@@ -104,7 +104,7 @@ void* pinned_alloc(size_t bytes) {
     }
   }
   void* p = nullptr;
-  cudaError_t e = cudaHostAlloc(&p, b, cudaHostAllocDefault);
+  cudaError_t e = cudaHostAlloc(&p, b, cudaHostAllocPortable)   /* results may be filled by several devices */;
   if (e != cudaSuccess) { set_error("pinned host allocation of %zu bytes failed: %s", b, cudaGetErrorString(e)); return nullptr; }
   std::lock_guard<std::mutex> lk(g_pin_mu);
   g_pin_size[p] = b;

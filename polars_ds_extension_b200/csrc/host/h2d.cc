@@ -1,0 +1,144 @@
+// Host -> device transport of the packer (replaces the memcpy into the Vec of series_to_slice_inner,
+// /root/reference/src/utils/mod.rs:101-206, by DMA into the device frame).
+//
+// Polars hands a plugin PAGEABLE Arrow buffers.  cudaMemcpyAsync on pageable memory goes through the driver's own
+// staging path (one thread, page by page) and reaches a fraction of the PCIe rate, so large pageable ranges are staged
+// here instead: W host threads copy 8 MiB pieces into a per-device ring of pinned slots (two per thread) and each
+// piece is DMA'd from its slot on the thread's own stream — memcpy of piece k+1 overlaps the DMA of piece k, and W
+// memcpy streams together exceed what one PCIe Gen5 x16 link carries.  Pinned sources (cudaHostAlloc /
+// cudaHostRegister) skip all of this.
+#include "../common.h"
+#include "host.h"
+#include <cstring>
+#include <cstdlib>
+#include <algorithm>
+#include <atomic>
+#include <map>
+
+namespace pdsb {
+
+namespace {
+
+constexpr size_t PIECE = size_t(8) << 20;
+constexpr size_t STAGE_MIN = size_t(1) << 20;      // smaller pageable ranges: the driver's path is fine
+constexpr int MAX_W = 16;
+
+struct StageRes {
+  void* slot[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t done = nullptr;
+  cudaStream_t st = nullptr;
+  bool used[2] = {false, false};
+};
+struct StagePool {
+  std::mutex mu;                  // one staged upload per device at a time (callers on other threads queue here)
+  std::vector<StageRes> res;
+  cudaEvent_t start = nullptr;
+};
+std::mutex g_pools_mu;
+std::map<int, std::unique_ptr<StagePool>> g_pools;
+
+StagePool* pool_for(int dev) {
+  std::lock_guard<std::mutex> lk(g_pools_mu);
+  auto& p = g_pools[dev];
+  if (!p) p.reset(new StagePool());
+  return p.get();
+}
+
+int ensure_res(StagePool* P, int w) {
+  if (!P->start) PDSB_CUDA_OK(cudaEventCreateWithFlags(&P->start, cudaEventDisableTiming));
+  while ((int)P->res.size() < w) {
+    StageRes r;
+    for (int i = 0; i < 2; ++i) {
+      PDSB_CUDA_OK(cudaHostAlloc(&r.slot[i], PIECE, cudaHostAllocPortable));
+      PDSB_CUDA_OK(cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming));
+    }
+    PDSB_CUDA_OK(cudaEventCreateWithFlags(&r.done, cudaEventDisableTiming));
+    PDSB_CUDA_OK(cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking));
+    P->res.push_back(r);
+  }
+  return 0;
+}
+
+int staging_threads() {
+  static int w = [] {
+    const char* e = getenv("PDS_B200_H2D_THREADS");
+    if (e && atoi(e) > 0) return std::min(MAX_W, atoi(e));
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    DeviceGroup* g = active_group();
+    const unsigned share = hw / (2 * (g ? (unsigned)g->devices.size() : 1u));
+    return (int)std::min<unsigned>(8, std::max<unsigned>(2, share));
+  }();
+  return w;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+struct Piece { char* dst; const char* src; size_t bytes; };
+thread_local size_t t_staged = 0;
+
+}  // namespace
+
+size_t h2d_last_staged_bytes() { return t_staged; }
+
+int h2d_execute(const std::vector<H2DSeg>& segs, cudaStream_t s) {
+  NvtxRange nv("pdsb:h2d");
+  t_staged = 0;
+  std::vector<Piece> pieces;
+  for (const H2DSeg& g : segs) {
+    if (!g.bytes) continue;
+    if (g.bytes < STAGE_MIN || is_pinned(g.src)) {
+      PDSB_CUDA_OK(cudaMemcpyAsync(g.dst, g.src, g.bytes, cudaMemcpyHostToDevice, s));
+      continue;
+    }
+    for (size_t off = 0; off < g.bytes; off += PIECE)
+      pieces.push_back({(char*)g.dst + off, (const char*)g.src + off, std::min(PIECE, g.bytes - off)});
+    t_staged += g.bytes;
+  }
+  if (pieces.empty()) return 0;
+  int dev = 0;
+  PDSB_CUDA_OK(cudaGetDevice(&dev));
+  StagePool* P = pool_for(dev);
+  std::lock_guard<std::mutex> lk(P->mu);
+  const int W = (int)std::min<size_t>(staging_threads(), pieces.size());
+  if (ensure_res(P, W)) return 1;
+  // destinations were allocated (stream-ordered) on `s`: the staging streams start after that point
+  PDSB_CUDA_OK(cudaEventRecord(P->start, s));
+  std::atomic<size_t> next{0};
+  std::atomic<int> failed{0};
+  std::vector<std::string> errs(W);
+  auto work = [&](int w) {
+    StageRes& R = P->res[w];
+    if (cudaSetDevice(dev) != cudaSuccess || cudaStreamWaitEvent(R.st, P->start, 0) != cudaSuccess) { failed = 1; errs[w] = "staging stream setup failed"; return; }
+    int k = 0;
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= pieces.size() || failed.load()) break;
+      const Piece& pc = pieces[i];
+      if (R.used[k] && cudaEventSynchronize(R.ev[k]) != cudaSuccess) { failed = 1; errs[w] = "staging event wait failed"; break; }
+      memcpy(R.slot[k], pc.src, pc.bytes);
+      cudaError_t e = cudaMemcpyAsync(pc.dst, R.slot[k], pc.bytes, cudaMemcpyHostToDevice, R.st);
+      if (e == cudaSuccess) e = cudaEventRecord(R.ev[k], R.st);
+      if (e != cudaSuccess) { failed = 1; errs[w] = std::string("staged H2D failed: ") + cudaGetErrorString(e); break; }
+      R.used[k] = true;
+      k ^= 1;
+    }
+    cudaEventRecord(R.done, R.st);
+  };
+  std::vector<std::thread> th;
+  for (int w = 1; w < W; ++w) th.emplace_back(work, w);
+  work(0);
+  for (auto& t : th) t.join();
+  for (int w = 0; w < W; ++w) PDSB_CUDA_OK(cudaStreamWaitEvent(s, P->res[w].done, 0));
+  if (failed.load()) {
+    for (auto& e : errs) if (!e.empty()) { set_error("%s", e.c_str()); break; }
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace pdsb

@@ -14,6 +14,7 @@
 #include <cfloat>
 #include <strings.h>
 #include <algorithm>
+#include <functional>
 
 namespace pdsb {
 
@@ -72,10 +73,15 @@ int64_t col_len(const pdsb_column& c) {
 int64_t chunk_nulls(const pdsb_chunk& ch) {
   if (!ch.validity || ch.length == 0) return 0;
   int64_t valid = 0;
-  for (int64_t i = 0; i < ch.length; ++i) {
-    int64_t b = ch.offset + i;
-    valid += (ch.validity[b >> 3] >> (b & 7)) & 1;
-  }
+  int64_t b = ch.offset;
+  const int64_t end = ch.offset + ch.length;
+  for (; b < end && (b & 7); ++b) valid += (ch.validity[b >> 3] >> (b & 7)) & 1;       // head bits
+  const int64_t full_end = b + ((end - b) & ~int64_t(7));
+  const uint8_t* v = ch.validity + (b >> 3);
+  int64_t nbytes = (full_end - b) >> 3;
+  while (nbytes >= 8) { uint64_t w; memcpy(&w, v, 8); valid += __builtin_popcountll(w); v += 8; nbytes -= 8; }
+  while (nbytes-- > 0) valid += __builtin_popcount(*v++);
+  for (b = full_end; b < end; ++b) valid += (ch.validity[b >> 3] >> (b & 7)) & 1;      // tail bits
   return ch.length - valid;
 }
 
@@ -100,9 +106,22 @@ struct DevBag {
   }
 };
 
+// All host->device copies of one frame are collected first and executed together (h2d.cc: pinned sources DMA directly,
+// pageable sources are staged by several host threads); kernels that consume uploaded raw bytes run afterwards.
+struct UploadPlan {
+  std::vector<H2DSeg> segs;
+  std::vector<std::function<int()>> after;      // K1 launches that read the uploaded raw / validity bytes
+  int run(cudaStream_t s) {
+    if (h2d_execute(segs, s)) return 1;
+    for (auto& f : after) if (f()) return 1;
+    segs.clear(); after.clear();
+    return 0;
+  }
+};
+
 // Upload one column into dst[0..n) as T.  mode: 0 null->NaN, 1 null->fill, 2 null->0
 template <typename T>
-int upload_column(const pdsb_column& c, T* dst, int mode, double fill, DevBag& bag, cudaStream_t s) {
+int upload_column(const pdsb_column& c, T* dst, int mode, double fill, DevBag& bag, UploadPlan& plan, cudaStream_t s) {
   int64_t off = 0;
   for (int i = 0; i < c.n_chunks; ++i) {
     const pdsb_chunk& ch = c.chunks[i];
@@ -110,7 +129,7 @@ int upload_column(const pdsb_column& c, T* dst, int mode, double fill, DevBag& b
     const bool has_null = ch.validity && (c.null_count != 0) && chunk_nulls(ch) > 0;
     if (c.dtype == DT<T>::code && !has_null) {
       const T* src = reinterpret_cast<const T*>(ch.data) + ch.offset;
-      PDSB_CUDA_OK(cudaMemcpyAsync(dst + off, src, (size_t)ch.length * sizeof(T), cudaMemcpyHostToDevice, s));
+      plan.segs.push_back({dst + off, src, (size_t)ch.length * sizeof(T)});
     } else {
       size_t esz = dtype_size(c.dtype);
       const uint8_t* raw;
@@ -125,15 +144,16 @@ int upload_column(const pdsb_column& c, T* dst, int mode, double fill, DevBag& b
       }
       uint8_t* d_raw = bag.alloc<uint8_t>(raw_bytes + 16);
       if (!d_raw) return 1;
-      PDSB_CUDA_OK(cudaMemcpyAsync(d_raw, raw, raw_bytes, cudaMemcpyHostToDevice, s));
+      plan.segs.push_back({d_raw, raw, raw_bytes});
       uint8_t* d_val = nullptr;
       if (has_null) {
         size_t vb = (size_t)((bit_off + ch.length + 7) >> 3);
         d_val = bag.alloc<uint8_t>(vb + 16);
         if (!d_val) return 1;
-        PDSB_CUDA_OK(cudaMemcpyAsync(d_val, ch.validity + (ch.offset >> 3), vb, cudaMemcpyHostToDevice, s));
+        plan.segs.push_back({d_val, ch.validity + (ch.offset >> 3), vb});
       }
-      if (pack_chunk<T>(d_raw, c.dtype, d_val, bit_off, ch.length, dst + off, mode, fill, s)) return 1;
+      const int dt = c.dtype; const int64_t len = ch.length; T* out = dst + off;
+      plan.after.push_back([=] { return pack_chunk<T>(d_raw, dt, d_val, bit_off, len, out, mode, fill, s); });
     }
     off += ch.length;
   }
@@ -142,7 +162,7 @@ int upload_column(const pdsb_column& c, T* dst, int mode, double fill, DevBag& b
 
 // rowmask[i] = 0 where column c is null
 template <typename T>
-int mask_column(const pdsb_column& c, T* rowmask, DevBag& bag, cudaStream_t s) {
+int mask_column(const pdsb_column& c, T* rowmask, DevBag& bag, UploadPlan& plan, cudaStream_t s) {
   int64_t off = 0;
   for (int i = 0; i < c.n_chunks; ++i) {
     const pdsb_chunk& ch = c.chunks[i];
@@ -151,8 +171,9 @@ int mask_column(const pdsb_column& c, T* rowmask, DevBag& bag, cudaStream_t s) {
       size_t vb = (size_t)((bit_off + ch.length + 7) >> 3);
       uint8_t* d_val = bag.alloc<uint8_t>(vb + 16);
       if (!d_val) return 1;
-      PDSB_CUDA_OK(cudaMemcpyAsync(d_val, ch.validity + (ch.offset >> 3), vb, cudaMemcpyHostToDevice, s));
-      if (and_validity<T>(d_val, bit_off, ch.length, rowmask + off, s)) return 1;
+      plan.segs.push_back({d_val, ch.validity + (ch.offset >> 3), vb});
+      const int64_t len = ch.length; T* rm = rowmask + off;
+      plan.after.push_back([=] { return and_validity<T>(d_val, bit_off, len, rm, s); });
     }
     off += ch.length;
   }
@@ -237,63 +258,171 @@ int build_frame(const pdsb_column* cols, int n_cols, int n_targets, const pdsb_c
       }
     }
   }
+  NvtxRange nv("pdsb:build_frame");
+  UploadPlan plan;
   F.Z = bag.alloc<T>((size_t)F.ld * n_cols);
   if (!F.Z) return 1;
   for (int c = 0; c < n_cols; ++c)
-    if (upload_column<T>(cols[c], F.Z + (size_t)c * F.ld, mode[c], fill, bag, s)) return 1;
+    if (upload_column<T>(cols[c], F.Z + (size_t)c * F.ld, mode[c], fill, bag, plan, s)) return 1;
   if (need_mask) {
     F.mask = bag.alloc<T>((size_t)F.ld);
     if (!F.mask) return 1;
     if (fill_value<T>(F.mask, n, T(1), s)) return 1;
     for (int c = 0; c < n_cols; ++c)
-      if (masks[c] && mask_column<T>(cols[c], F.mask, bag, s)) return 1;
-    for (int c = 0; c < n_cols; ++c)
-      if (zero_masked<T>(F.Z + (size_t)c * F.ld, F.mask, n, s)) return 1;
+      if (masks[c] && mask_column<T>(cols[c], F.mask, bag, plan, s)) return 1;
   }
   if (wcol) {
     if (col_len(*wcol) != n) { set_error("Shape of weights is not the same as the data."); return 1; }
     F.w = bag.alloc<T>((size_t)F.ld);
     if (!F.w) return 1;
-    if (upload_column<T>(*wcol, F.w, 0, 0.0, bag, s)) return 1;
+    if (upload_column<T>(*wcol, F.w, 0, 0.0, bag, plan, s)) return 1;
   }
+  if (plan.run(s)) return 1;
+  if (need_mask)
+    for (int c = 0; c < n_cols; ++c)
+      if (zero_masked<T>(F.Z + (size_t)c * F.ld, F.mask, n, s)) return 1;
   return 0;
+}
+
+// ---- row slices of Arrow-style columns (zero-copy: chunk views with adjusted offset / length) ----
+struct ColSlice {
+  std::vector<pdsb_column> cols;
+  std::vector<std::vector<pdsb_chunk>> chunks;
+};
+void slice_columns(const pdsb_column* cols, int n_cols, int64_t r0, int64_t r1, ColSlice& out) {
+  out.cols.assign(cols, cols + n_cols);
+  out.chunks.assign(n_cols, {});
+  for (int c = 0; c < n_cols; ++c) {
+    int64_t pos = 0;
+    for (int k = 0; k < cols[c].n_chunks; ++k) {
+      const pdsb_chunk& ch = cols[c].chunks[k];
+      const int64_t lo = std::max(r0, pos), hi = std::min(r1, pos + ch.length);
+      if (hi > lo) { pdsb_chunk v = ch; v.offset = ch.offset + (lo - pos); v.length = hi - lo; out.chunks[c].push_back(v); }
+      pos += ch.length;
+    }
+    out.cols[c].n_chunks = (int)out.chunks[c].size();
+    out.cols[c].chunks = out.chunks[c].data();
+    if (out.cols[c].null_count != 0) out.cols[c].null_count = -1;      // recount inside the slice
+  }
+}
+
+// One row shard of a lin_reg call: everything that lives on ONE device.
+template <typename T>
+struct LrShard {
+  int64_t r0 = 0, r1 = 0;
+  ColSlice data, w;
+  cudaStream_t s = nullptr;
+  std::unique_ptr<DevBag> bag;
+  Frame<T> F;
+  double* dM = nullptr; double* dbeta = nullptr; double* daux = nullptr; int* dstatus = nullptr;
+  T* dpred = nullptr; T* dresid = nullptr; uint8_t* dvalid = nullptr;
+  std::vector<double> hbeta, haux;
+  int hstatus = 0;
+  double hcount = 0.0;
+  std::string err;
+};
+
+struct LrPlan {       // what every shard needs to know about the call
+  NullPolicy pol; bool multi, weighted; int n_targets, want_pred, w_rcond;
+  pdsb_solve_opts o; int p, t, q, q1;
+};
+
+// phase 1 (on the shard's device): null policy + upload + partial moments
+template <typename T>
+int shard_moments(LrShard<T>& S, const LrPlan& P) {
+  NvtxRange nv("pdsb:shard_moments");
+  cudaStream_t s2;
+  if (thread_streams(&S.s, &s2)) return 1;
+  S.bag.reset(new DevBag(S.s));
+  const pdsb_column* wcol = P.weighted ? &S.w.cols[0] : nullptr;
+  if (build_frame<T>(S.data.cols.data(), (int)S.data.cols.size(), P.n_targets, wcol, P.pol, P.multi, false, S.F, *S.bag, S.s)) return 1;
+  S.dM = S.bag->template alloc<double>((size_t)P.q1 * P.q1);
+  S.dbeta = S.bag->template alloc<double>((size_t)P.q * P.t);
+  S.daux = S.bag->template alloc<double>((size_t)P.q * P.q + P.q);
+  S.dstatus = S.bag->template alloc<int>(4);
+  if (!S.dM || !S.dbeta || !S.daux || !S.dstatus) return 1;
+  if (moments_any<T>(S.F.X(), S.F.ld, S.F.Y(), S.F.ld, S.F.w, S.F.mask, S.F.n, P.p, P.t, S.dM, S.s)) return 1;
+  return 0;
+}
+
+// phase 2: [all-reduce of the moments] -> solve -> predict the shard -> D2H into the caller's buffers
+template <typename T>
+int shard_finish(LrShard<T>& S, const LrPlan& P, DeviceGroup* grp, int idx, bool world, T* hp, T* hr, uint8_t* hv,
+                 int64_t n_total) {
+  NvtxRange nv("pdsb:shard_finish");
+  cudaStream_t s = S.s;
+  const size_t mcount = (size_t)P.q1 * P.q1;
+  if (grp && group_allreduce_f64(grp, idx, S.dM, mcount, s)) return 1;      // NVLink: k x (p+t+1)^2 f64
+  if (world && world_allreduce_f64(S.dM, mcount, s)) return 1;
+  if (solve_from_moments(S.dM, P.o, S.dbeta, S.dstatus, P.w_rcond ? S.daux : nullptr, s)) return 1;
+  S.hbeta.resize((size_t)P.q * P.t); S.haux.resize(P.q);
+  PDSB_CUDA_OK(cudaMemcpyAsync(S.hbeta.data(), S.dbeta, S.hbeta.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  PDSB_CUDA_OK(cudaMemcpyAsync(&S.hstatus, S.dstatus, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PDSB_CUDA_OK(cudaMemcpyAsync(&S.hcount, S.dM + mcount - 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (P.w_rcond) PDSB_CUDA_OK(cudaMemcpyAsync(S.haux.data(), S.daux, P.q * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (P.want_pred) {
+    const Frame<T>& F = S.F;
+    S.dpred = S.bag->template alloc<T>((size_t)F.ld * P.t);
+    S.dresid = S.bag->template alloc<T>((size_t)F.ld * P.t);
+    S.dvalid = S.bag->template alloc<uint8_t>((size_t)F.ld);
+    if (!S.dpred || !S.dresid || !S.dvalid) return 1;
+    if (predict_resid<T>(F.X(), F.ld, F.Y(), F.ld, nullptr, F.mask, F.n, P.p, P.t, P.o.add_bias, S.dbeta, S.dstatus, S.dpred,
+                         S.dresid, F.ld, S.dvalid, nullptr, s)) return 1;
+    for (int k = 0; k < P.t; ++k) {
+      PDSB_CUDA_OK(cudaMemcpyAsync(hp + (size_t)k * n_total + S.r0, S.dpred + (size_t)k * F.ld, (size_t)F.n * sizeof(T), cudaMemcpyDeviceToHost, s));
+      PDSB_CUDA_OK(cudaMemcpyAsync(hr + (size_t)k * n_total + S.r0, S.dresid + (size_t)k * F.ld, (size_t)F.n * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+    if (hv) PDSB_CUDA_OK(cudaMemcpyAsync(hv + S.r0, S.dvalid, (size_t)F.n, cudaMemcpyDeviceToHost, s));
+  }
+  PDSB_CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int64_t shard_min_rows() {
+  static int64_t v = [] { const char* e = getenv("PDS_B200_SHARD_MIN_ROWS"); return e && atoll(e) > 0 ? atoll(e) : (int64_t)1 << 21; }();
+  return v;
 }
 
 template <typename T>
 int host_lin_reg_t(const pdsb_column* cols, int n_cols, const pdsb_lr_kwargs* kw, int n_targets, int want_pred,
                    int w_rcond, pdsb_host_result* out) {
-  cudaStream_t s, s2;
-  if (thread_streams(&s, &s2)) return 1;
-  NullPolicy pol;
-  if (parse_null_policy(kw->null_policy, &pol)) return 1;
-  const bool multi = n_targets > 1;
-  const bool weighted = kw->weighted && !multi && !w_rcond;
-  const pdsb_column* wcol = weighted ? &cols[0] : nullptr;
-  const pdsb_column* data = weighted ? cols + 1 : cols;
-  const int n_data = weighted ? n_cols - 1 : n_cols;
-  DevBag bag(s);
-  Frame<T> F;
-  if (build_frame<T>(data, n_data, n_targets, wcol, pol, multi, false, F, bag, s)) return 1;
-  const int p = F.p, t = F.t;
+  NvtxRange nv("pdsb:host_lin_reg");
+  LrPlan P{};
+  if (parse_null_policy(kw->null_policy, &P.pol)) return 1;
+  P.multi = n_targets > 1;
+  P.weighted = kw->weighted && !P.multi && !w_rcond;
+  P.n_targets = n_targets; P.want_pred = want_pred; P.w_rcond = w_rcond;
+  const pdsb_column* wcol = P.weighted ? &cols[0] : nullptr;
+  const pdsb_column* data = P.weighted ? cols + 1 : cols;
+  const int n_data = P.weighted ? n_cols - 1 : n_cols;
+  if (n_data < n_targets + 1) { set_error("Data is empty"); return 1; }
+  const int64_t n = col_len(data[0]);
+  for (int c = 1; c < n_data; ++c)
+    if (col_len(data[c]) != n) { set_error("Seires don't have the same length."); return 1; }
+  if (n == 0) { set_error("Empty data"); return 1; }
+  if (wcol && col_len(*wcol) != n) { set_error("Shape of weights is not the same as the data."); return 1; }
+  const int p = n_data - n_targets, t = n_targets;
   const int add_bias = kw->bias ? 1 : 0;
   const int q = p + add_bias;
   if (p < 1) { set_error("Data is empty"); return 1; }
-  if (!multi && !F.mask && F.n < q) { set_error("#Data < #features. No conclusive result."); return 1; }
+  P.p = p; P.t = t; P.q = q; P.q1 = p + t + 1;
 
-  pdsb_solve_opts o{};
+  pdsb_solve_opts& o = P.o;
   o.p = p; o.t = t; o.add_bias = add_bias; o.solver = solver_from_string(kw->solver);
   o.l1_reg = kw->l1_reg; o.l2_reg = kw->l2_reg; o.tol = kw->tol; o.singular_x_tol = kw->singular_x_tol;
   o.positive = kw->positive; o.max_iter = (int)kw->max_iter;
   const bool is_f32 = sizeof(T) == 4;
+  const int world = world_enabled() ? world_size() : 1;
   if (w_rcond) {
     o.method = PDSB_METHOD_RCOND;
     const double eps = is_f32 ? (double)FLT_EPSILON : DBL_EPSILON;
     double rc = is_f32 ? (double)(float)kw->tol : kw->tol;
-    o.tol = std::max(rc, eps * (double)std::max<int64_t>(F.n, q));
+    // with a world communicator n is this rank's share; the threshold only needs max(n_total, q) to the scale of eps
+    o.tol = std::max(rc, eps * (double)std::max<int64_t>(n * world, q));
     o.singular_x_tol = 0.0;
-  } else if (weighted) {
+  } else if (P.weighted) {
     o.method = PDSB_METHOD_LSTSQ; o.l2_reg = 0.0; o.singular_x_tol = 0.0;   // faer_weighted_lr: no ridge, no gate
-  } else if (multi) {
+  } else if (P.multi) {
     o.method = PDSB_METHOD_LSTSQ; o.l1_reg = 0.0;
   } else {
     const bool l1 = kw->l1_reg > 0.0, l2 = kw->l2_reg > 0.0;
@@ -305,68 +434,73 @@ int host_lin_reg_t(const pdsb_column* cols, int n_cols, const pdsb_lr_kwargs* kw
       if (is_f32) o.max_iter = 2000;
     }
   }
-  const int q1 = p + t + 1;
-  double* dM = bag.alloc<double>((size_t)q1 * q1);
-  double* dbeta = bag.alloc<double>((size_t)q * t);
-  double* daux = bag.alloc<double>((size_t)q * q + q);
-  int* dstatus = bag.alloc<int>(4);
-  if (!dM || !dbeta || !daux || !dstatus) return 1;
-  if (moments_any<T>(F.X(), F.ld, F.Y(), F.ld, F.w, F.mask, F.n, p, t, dM, s)) return 1;
-  if (solve_from_moments(dM, o, dbeta, dstatus, w_rcond ? daux : nullptr, s)) return 1;
 
-  std::vector<double> hbeta((size_t)q * t), haux(q);
-  int hstatus = 0;
-  double hcount = 0.0;
-  PDSB_CUDA_OK(cudaMemcpyAsync(hbeta.data(), dbeta, hbeta.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-  PDSB_CUDA_OK(cudaMemcpyAsync(&hstatus, dstatus, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PDSB_CUDA_OK(cudaMemcpyAsync(&hcount, dM + (size_t)q1 * q1 - 1, sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (w_rcond) PDSB_CUDA_OK(cudaMemcpyAsync(haux.data(), daux, q * sizeof(double), cudaMemcpyDeviceToHost, s));
+  // ---- shards: one per device of the active group when the call is big enough to pay for it ----
+  DeviceGroup* grp = (n >= shard_min_rows()) ? active_group() : nullptr;
+  if (grp && world > 1) { set_error("a device group (PDS_B200_DEVICES) and a world communicator cannot be combined"); return 1; }
+  const int k = grp ? (int)grp->devices.size() : 1;
+  std::vector<LrShard<T>> sh(k);
+  for (int i = 0; i < k; ++i) {
+    // contiguous row ranges, boundaries on multiples of 1024 rows (whole stages of the Gram kernel)
+    auto cut = [&](int j) { return j >= k ? n : std::min<int64_t>(n, ((n * j / k) + 1023) / 1024 * 1024); };
+    sh[i].r0 = cut(i); sh[i].r1 = cut(i + 1);
+    if (k == 1) {
+      sh[i].data.cols.assign(data, data + n_data);
+      if (wcol) sh[i].w.cols.assign(wcol, wcol + 1);
+    } else {
+      slice_columns(data, n_data, sh[i].r0, sh[i].r1, sh[i].data);
+      if (wcol) slice_columns(wcol, 1, sh[i].r0, sh[i].r1, sh[i].w);
+    }
+  }
+  auto run_all = [&](const std::function<int(int)>& fn) -> int {
+    if (k == 1) { int rc = fn(0); if (rc) sh[0].err = get_error(); return rc; }
+    std::vector<std::future<int>> fu;
+    for (int i = 0; i < k; ++i)
+      fu.push_back(grp->workers[i]->submit([&, i] { int rc = fn(i); if (rc) sh[i].err = get_error(); return rc; }));
+    int rc = 0;
+    for (auto& f : fu) rc |= f.get();
+    return rc;
+  };
+  auto first_error = [&] { for (auto& S : sh) if (!S.err.empty()) { set_error("%s", S.err.c_str()); return; } };
+  // device scratch is released on the thread (device) that made it
+  struct Cleanup { std::function<void()> f; ~Cleanup() { f(); } } cleanup{[&] { run_all([&](int i) { sh[i].bag.reset(); return 0; }); }};
 
-  T* dpred = nullptr; T* dresid = nullptr; uint8_t* dvalid = nullptr;
-  if (want_pred) {
-    dpred = bag.alloc<T>((size_t)F.ld * t);
-    dresid = bag.alloc<T>((size_t)F.ld * t);
-    dvalid = bag.alloc<uint8_t>((size_t)F.ld);
-    if (!dpred || !dresid || !dvalid) return 1;
-    if (predict_resid<T>(F.X(), F.ld, F.Y(), F.ld, nullptr, F.mask, F.n, p, t, add_bias, dbeta, dstatus, dpred, dresid,
-                         F.ld, dvalid, nullptr, s)) return 1;
-  }
-  PDSB_CUDA_OK(cudaStreamSynchronize(s));
-  if (F.mask) {
-    const int64_t n_valid = (int64_t)llround(hcount);
-    if (!multi && n_valid < q) { set_error("#Data < #features. No conclusive result."); return 1; }
-    if (weighted && n_valid != F.n) { set_error("Shape of weights is not the same as the data."); return 1; }
-  }
+  if (run_all([&](int i) { return sh[i].r1 > sh[i].r0 || k == 1 ? shard_moments<T>(sh[i], P) : (set_error("empty shard"), 1); })) { first_error(); return 1; }
+  bool any_mask = false;
+  for (auto& S : sh) any_mask |= S.F.mask != nullptr;
+  if (!P.multi && !any_mask && world == 1 && n < q) { set_error("#Data < #features. No conclusive result."); return 1; }
+
   memset(out, 0, sizeof(*out));
-  out->is_f32 = is_f32; out->n_coef = q; out->n_targets = t; out->gated = hstatus != 0; out->n_rows = want_pred ? F.n : 0;
+  T* hp = nullptr; T* hr = nullptr; uint8_t* hv = nullptr;
+  if (want_pred) {
+    hp = reinterpret_cast<T*>(result_buf(out, (size_t)n * t * sizeof(T)));
+    hr = reinterpret_cast<T*>(result_buf(out, (size_t)n * t * sizeof(T)));
+    if (any_mask) hv = reinterpret_cast<uint8_t*>(result_buf(out, (size_t)n));
+    if (!hp || !hr || (any_mask && !hv)) return 1;
+  }
+  if (run_all([&](int i) { return shard_finish<T>(sh[i], P, grp, i, world > 1, hp, hr, hv, n); })) { first_error(); return 1; }
+
+  const LrShard<T>& S0 = sh[0];
+  if (any_mask || world > 1) {
+    const int64_t n_valid = (int64_t)llround(S0.hcount);        // the reduced moments hold the global row count
+    if (!P.multi && n_valid < q) { set_error("#Data < #features. No conclusive result."); return 1; }
+    if (P.weighted && world == 1 && n_valid != n) { set_error("Shape of weights is not the same as the data."); return 1; }
+  }
+  out->is_f32 = is_f32; out->n_coef = q; out->n_targets = t; out->gated = S0.hstatus != 0; out->n_rows = want_pred ? n : 0;
   if (!want_pred) {
     T* c = reinterpret_cast<T*>(result_buf(out, (size_t)q * t * sizeof(T)));
     if (!c) return 1;
-    for (size_t i = 0; i < (size_t)q * t; ++i) c[i] = (T)hbeta[i];
+    for (size_t i = 0; i < (size_t)q * t; ++i) c[i] = (T)S0.hbeta[i];
     out->coeffs = c;
     if (w_rcond) {
       T* sv = reinterpret_cast<T*>(result_buf(out, (size_t)q * sizeof(T)));
       if (!sv) return 1;
-      for (int i = 0; i < q; ++i) sv[i] = (T)haux[i];
+      for (int i = 0; i < q; ++i) sv[i] = (T)S0.haux[i];
       out->singular_values = sv;
     }
     return 0;
   }
-  T* hp = reinterpret_cast<T*>(result_buf(out, (size_t)F.n * t * sizeof(T)));
-  T* hr = reinterpret_cast<T*>(result_buf(out, (size_t)F.n * t * sizeof(T)));
-  if (!hp || !hr) return 1;
-  for (int k = 0; k < t; ++k) {
-    PDSB_CUDA_OK(cudaMemcpyAsync(hp + (size_t)k * F.n, dpred + (size_t)k * F.ld, (size_t)F.n * sizeof(T), cudaMemcpyDeviceToHost, s));
-    PDSB_CUDA_OK(cudaMemcpyAsync(hr + (size_t)k * F.n, dresid + (size_t)k * F.ld, (size_t)F.n * sizeof(T), cudaMemcpyDeviceToHost, s));
-  }
-  if (F.mask || hstatus != 0) {
-    uint8_t* hv = reinterpret_cast<uint8_t*>(result_buf(out, (size_t)F.n));
-    if (!hv) return 1;
-    PDSB_CUDA_OK(cudaMemcpyAsync(hv, dvalid, (size_t)F.n, cudaMemcpyDeviceToHost, s));
-    out->valid = hv;
-  }
-  PDSB_CUDA_OK(cudaStreamSynchronize(s));
-  out->pred = hp; out->resid = hr;
+  out->pred = hp; out->resid = hr; out->valid = hv;
   return 0;
 }
 

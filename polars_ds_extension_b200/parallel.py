@@ -13,6 +13,46 @@ import torch
 import torch.distributed as dist
 
 
+def set_devices(devices) -> None:
+    """Single process, several GPUs: every large lin_reg call of this process is row-sharded over `devices`
+    (include/pdsb.h, pdsb_set_devices; the environment variable PDS_B200_DEVICES does the same at load time)."""
+    import ctypes as C
+
+    from ._lib import check, lib
+
+    d = list(devices)
+    arr = (C.c_int * max(len(d), 1))(*d)
+    check(lib().pdsb_set_devices(arr, len(d)))
+
+
+def init_world() -> int:
+    """One process per GPU (torchrun): join the library's own NCCL communicator.  Rank 0 creates the 128-byte id,
+    torch.distributed (whatever backend the launcher initialised) carries it to the other ranks, every rank joins.
+    From here on plugin lin_reg calls are collective: one fit over the rows of all ranks.  Returns the world size."""
+    import ctypes as C
+
+    from ._lib import check, lib
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 1
+    world, rank = dist.get_world_size(), dist.get_rank()
+    buf = (C.c_uint8 * 128)()
+    if rank == 0:
+        check(lib().pdsb_comm_unique_id(buf))
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    raw = bytes(t.cpu().tolist())
+    check(lib().pdsb_comm_init_rank(world, rank, C.create_string_buffer(raw, 128)))
+    return world
+
+
+def destroy_world() -> None:
+    from ._lib import lib
+
+    lib().pdsb_comm_destroy()
+
+
 def shard_rows(n: int, rank: int, world: int, align: int = 128) -> Tuple[int, int]:
     """Contiguous [begin, end) row range of `rank`; boundaries are multiples of `align` (frame blocks) except the last."""
     blocks = (n + align - 1) // align

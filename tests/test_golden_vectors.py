@@ -20,13 +20,19 @@ def _frame(X=None, **extra):
     return Frame(d)
 
 
-def _check(be, f32):
+def _check(be, f32, errs=None):
+    """`errs` (optional list) receives the vector-relative error of every compared quantity, in call order."""
     import polars_ds_extension_b200.config as cfg
 
     assert cfg.LIN_REG_EXPR_F64 == (not f32)
     tol = 2e-4 if f32 else 1e-8
     df = _frame()
-    close = lambda a, b, t=tol: np.testing.assert_allclose(np.asarray(a, dtype=np.float64), b, rtol=t, atol=t)
+
+    def close(a, b, t=tol):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        if errs is not None:
+            errs.append(float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)))
+        np.testing.assert_allclose(a, b, rtol=t, atol=t)
     close(be.eval(df, pds.lin_reg(*FEATS, target="y", add_bias=True)), G["ols_bias"])
     close(be.eval(df, pds.lin_reg(*FEATS, target="y")), G["ols"])
     close(be.eval(df, pds.lin_reg(*FEATS, target="y", add_bias=True, l2_reg=0.1)), G["ridge_bias"], max(tol, 1e-7))
@@ -80,7 +86,17 @@ def test_cuda_matches_golden(f32, monkeypatch):
     from tests.backends import PluginBackend
 
     monkeypatch.setattr(cfg, "LIN_REG_EXPR_F64", not f32)
-    _check(PluginBackend(), f32)
+    eg, eo = [], []
+    _check(PluginBackend(), f32, eg)
+    if f32:
+        # SURVEY.md §8c, second half of the f32 rule: against the frozen (sklearn / numpy / scipy) answers the CUDA path
+        # must be no farther off than the f32 oracle is — whatever absolute tolerance the shared checks above allow
+        from tests.backends import OracleBackend
+
+        _check(OracleBackend(), f32, eo)
+        assert len(eg) == len(eo)
+        worse = [(i, g, o) for i, (g, o) in enumerate(zip(eg, eo)) if g > max(o, 2e-6)]
+        assert not worse, worse
     be = PluginBackend()
     fast = be.group_eval(_frame(), "k", pds.lin_reg(*FEATS, target="y", add_bias=True), fast=True)
     np.testing.assert_allclose(np.vstack(fast), G["grouped_bias"], rtol=5e-3 if f32 else 1e-7, atol=5e-3 if f32 else 1e-7)
