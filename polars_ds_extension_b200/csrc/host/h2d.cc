@@ -67,7 +67,7 @@ int staging_threads() {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     DeviceGroup* g = active_group();
     const unsigned share = hw / (2 * (g ? (unsigned)g->devices.size() : 1u));
-    return (int)std::min<unsigned>(8, std::max<unsigned>(2, share));
+    return (int)std::min<unsigned>(MAX_W, std::max<unsigned>(2, share));
   }();
   return w;
 }

@@ -30,6 +30,7 @@
 // Bytes per row (algorithmic): (p+1) s read, (p+bias) s + s + 1 written.
 #include "../common.h"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace pdsb {
 
@@ -388,6 +389,507 @@ online_main_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y
   }
 }
 
+// =====================================================================================================================
+// Pass C, f32, packed: the production kernel of rolling / recursive for float data (D <= 12).
+//
+// ncu on the kernel above (profiles/README.md, round 1): issue-slot-bound at ~40 warp-instructions per row — the f64
+// lane-per-moment walk (4 LDS + 4 DFMA per row), the staging of e-vectors as doubles, and a 32-wide Cholesky.  This
+// version does the same mathematics with a quarter of the instructions:
+//   * a warp takes 64 rows per step and every lane owns the ADJACENT row pair (2l, 2l+1): all per-row arithmetic is
+//     packed f32x2 (FFMA2 / FMUL2 / FADD2, sm_100), so products, window sums, the Cholesky and the prediction of two rows
+//     cost one instruction stream;
+//   * moments of a step are formed as products  m_k(t) = e_a e_b - l_a l_b  by the row lanes (2 packed instructions per
+//     moment per 2 rows), written to shared memory [moment][row], and turned into running sums by lane-per-moment serial
+//     scans over the 64 rows (LDS.128 / 4 FADD / STS.128) — in f32, from zero, so the rounding is that of a 64-term sum;
+//   * f64 lives only at step boundaries: each moment lane keeps the exact-to-f64 base W_k (chain prefix from passes A/B
+//     plus the step totals) and publishes it as f32 once per step;  W_t = base + scan(t)  is formed by the row lanes.
+// The Gram the solver sees is an f32 rounding of the window moments, exactly as before (the old kernel cast its f64
+// walk to T before the solve); what changes is 12 instead of 40 warp-instructions per row.
+// =====================================================================================================================
+constexpr int SB = 64;                   // rows per step of the packed kernel
+constexpr int SBP = 68;                  // row stride of the product tile: 272 B = 16 (mod 128) -> conflict-free LDS.128 scans
+constexpr int V2_WARPS = 4;
+
+template <int D> struct V2 {
+  static constexpr int NG = D * (D + 1) / 2;
+  static constexpr int NM = NG + D + 1;
+  static constexpr int TPL = (NM + 31) / 32;
+  static constexpr int NB = (NM + 3) & ~3;
+  static constexpr size_t warp_floats = (size_t)NM * SBP + NB;
+};
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
+
+// raw pair load (rows r, r+1; clamped addresses, no branches); z[D] (features, ones for the bias slot) and y
+template <int D>
+__device__ __forceinline__ void load_pair(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, int p,
+                                          int64_t r, int64_t n, float2* z, float2& yv) {
+  const int64_t r0 = min(max(r, (int64_t)0), n - 1), r1 = min(max(r + 1, (int64_t)0), n - 1);
+  const float* q = X;
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    if (c < p) { z[c] = f2(__ldg(q + r0), __ldg(q + r1)); q += ldx; }
+    else z[c] = f2(1.0f, 1.0f);
+  }
+  yv = f2(__ldg(y + r0), __ldg(y + r1));
+}
+
+// e-vector pair: zero where the row is missing or holds a non-finite value; fin = 1 / 0 per row
+template <int D>
+__device__ __forceinline__ void finish_pair(float2* z, float2& yv, bool in0, bool in1, float2& fin) {
+  float2 acc = __fmul2_rn(yv, bc(0.0f));
+#pragma unroll
+  for (int c = 0; c < D; ++c) acc = __ffma2_rn(z[c], bc(0.0f), acc);      // 0 when every entry is finite, NaN otherwise
+  const bool k0 = in0 && (acc.x == 0.0f), k1 = in1 && (acc.y == 0.0f);
+  fin = f2(k0 ? 1.0f : 0.0f, k1 ? 1.0f : 0.0f);
+#pragma unroll
+  for (int c = 0; c < D; ++c) z[c] = f2(k0 ? z[c].x : 0.0f, k1 ? z[c].y : 0.0f);
+  yv = f2(k0 ? yv.x : 0.0f, k1 ? yv.y : 0.0f);
+}
+
+// row lanes: products of one step -> tile[k][2 lane .. 2 lane + 1]
+template <int D, bool BOTH>
+__device__ __forceinline__ void put_products(float* __restrict__ tile, int lane, const float2* e, float2 ey, float2 ef,
+                                             const float2* l, float2 ly, float2 lf) {
+  constexpr int NG = V2<D>::NG, NM = V2<D>::NM;
+  float2* out = reinterpret_cast<float2*>(tile) + lane;
+  constexpr int ST = SBP / 2;                                // stride in float2
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    float2 nli = BOTH ? __fmul2_rn(l[i], bc(-1.0f)) : bc(0.0f);
+#pragma unroll
+    for (int j = i; j < D; ++j) {
+      float2 m = BOTH ? __ffma2_rn(e[i], e[j], __fmul2_rn(nli, l[j])) : __fmul2_rn(e[i], e[j]);
+      out[(size_t)k * ST] = m;
+      ++k;
+    }
+    float2 my = BOTH ? __ffma2_rn(e[i], ey, __fmul2_rn(nli, ly)) : __fmul2_rn(e[i], ey);
+    out[(size_t)(NG + i) * ST] = my;
+  }
+  out[(size_t)(NM - 1) * ST] = BOTH ? __fadd2_rn(ef, __fmul2_rn(lf, bc(-1.0f))) : ef;
+}
+
+// moment lanes: in-place inclusive scan of the 64 rows of their moments; returns the step totals
+template <int D>
+__device__ __forceinline__ void scan_products(float* __restrict__ tile, int lane, float* tot) {
+  constexpr int NM = V2<D>::NM, TPL = V2<D>::TPL;
+  float s[TPL];
+  float4* row[TPL];
+#pragma unroll
+  for (int m = 0; m < TPL; ++m) {
+    s[m] = 0.0f;
+    const int k = min(lane + 32 * m, NM - 1);                // idle lanes rescan the last moment's row: harmless? no -> guarded below
+    row[m] = reinterpret_cast<float4*>(tile + (size_t)k * SBP);
+  }
+#pragma unroll 4
+  for (int i = 0; i < SB / 4; ++i) {
+#pragma unroll
+    for (int m = 0; m < TPL; ++m) {
+      if (lane + 32 * m < NM) {
+        float4 v = row[m][i];
+        s[m] += v.x; v.x = s[m];
+        s[m] += v.y; v.y = s[m];
+        s[m] += v.z; v.z = s[m];
+        s[m] += v.w; v.w = s[m];
+        row[m][i] = v;
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < TPL; ++m) tot[m] = s[m];
+}
+
+// packed Cholesky solve of two rows at once (same algorithm as chol_solve_packed)
+template <int D>
+__device__ __forceinline__ void chol_solve_pair(float2* g, float lambda, float2* beta, bool& ok0, bool& ok1) {
+  constexpr int NG = V2<D>::NG;
+#pragma unroll
+  for (int i = 0; i < D; ++i) { g[gidx<D>(i, i)] = __fadd2_rn(g[gidx<D>(i, i)], bc(lambda)); beta[i] = g[NG + i]; }
+  ok0 = ok1 = true;
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    const float2 d = g[gidx<D>(c, c)];
+    if (!(d.x > 0.0f) || !isfinite(d.x)) ok0 = false;
+    if (!(d.y > 0.0f) || !isfinite(d.y)) ok1 = false;
+    const float2 inv = f2(rsqrtf(d.x), rsqrtf(d.y));
+    g[gidx<D>(c, c)] = inv;
+#pragma unroll
+    for (int i = c + 1; i < D; ++i) g[gidx<D>(i, c)] = __fmul2_rn(g[gidx<D>(i, c)], inv);
+#pragma unroll
+    for (int j = c + 1; j < D; ++j) {
+      const float2 nj = __fmul2_rn(g[gidx<D>(j, c)], bc(-1.0f));
+#pragma unroll
+      for (int i = j; i < D; ++i) g[gidx<D>(i, j)] = __ffma2_rn(g[gidx<D>(i, c)], nj, g[gidx<D>(i, j)]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    float2 s = beta[i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) s = __ffma2_rn(__fmul2_rn(g[gidx<D>(i, j)], bc(-1.0f)), beta[j], s);
+    beta[i] = __fmul2_rn(s, g[gidx<D>(i, i)]);
+  }
+#pragma unroll
+  for (int i = D - 1; i >= 0; --i) {
+    float2 s = beta[i];
+#pragma unroll
+    for (int j = i + 1; j < D; ++j) s = __ffma2_rn(__fmul2_rn(g[gidx<D>(j, i)], bc(-1.0f)), beta[j], s);
+    beta[i] = __fmul2_rn(s, g[gidx<D>(i, i)]);
+  }
+}
+
+template <int D, bool ROLLING>
+__global__ void __launch_bounds__(V2_WARPS * 32)
+online_main_f32x2_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, int64_t n, int p,
+                         int64_t window, int64_t min_rows, int skip, float lambda, int64_t row0, int64_t nchains,
+                         const double* __restrict__ C /* [NM][nchains] exclusive chain prefixes */,
+                         float* __restrict__ coeffs, float* __restrict__ pred, uint8_t* __restrict__ valid) {
+  constexpr int NM = V2<D>::NM, TPL = V2<D>::TPL, NB = V2<D>::NB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t k = (int64_t)blockIdx.x * V2_WARPS + wid;
+  if (k >= nchains) return;
+  float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)wid * V2<D>::warp_floats;     // [NM][SBP]
+  float* basef = tile + (size_t)NM * SBP;                                                   // [NB]
+  const int64_t chain0 = k * CHAIN_ROWS;
+
+  // moment lanes: f64 base of "their" moments at the chain start
+  double W[TPL];
+#pragma unroll
+  for (int m = 0; m < TPL; ++m) W[m] = (lane + 32 * m < NM) ? C[(size_t)(lane + 32 * m) * nchains + k] : 0.0;
+  if (ROLLING) {
+    // rows [lo, chain0) are inside the window of the chain's first row: subtract the prefix up to lo = C[kl] + head
+    const int64_t lo = max((int64_t)0, chain0 - window);
+    const int64_t kl = lo / CHAIN_ROWS;
+#pragma unroll
+    for (int m = 0; m < TPL; ++m) if (lane + 32 * m < NM) W[m] -= C[(size_t)(lane + 32 * m) * nchains + kl];
+    for (int64_t rb = kl * CHAIN_ROWS; rb < lo; rb += SB) {       // empty when the window is a multiple of the chain
+      float2 z[D], yv, fin;
+      const int64_t r = rb + 2 * lane;
+      load_pair<D>(X, ldx, y, p, r, n, z, yv);
+      finish_pair<D>(z, yv, r < lo, r + 1 < lo, fin);
+      put_products<D, false>(tile, lane, z, yv, fin, z, yv, fin);
+      __syncwarp();
+      float tot[TPL];
+      scan_products<D>(tile, lane, tot);
+#pragma unroll
+      for (int m = 0; m < TPL; ++m) W[m] -= (double)tot[m];
+      __syncwarp();
+    }
+  }
+
+  // software pipeline: the raw rows of step b+1 are in flight while step b is scanned and solved
+  float2 zn[D], yn, zln[D], yln;
+  load_pair<D>(X, ldx, y, p, chain0 + 2 * lane, n, zn, yn);
+  if (ROLLING) load_pair<D>(X, ldx, y, p, chain0 + 2 * lane - window, n, zln, yln);
+  for (int b = 0; b < CHAIN_ROWS / SB; ++b) {
+    const int64_t rb = chain0 + (int64_t)b * SB;
+    if (rb >= n) break;
+    const int64_t r = rb + 2 * lane;
+    // ---- row lanes: products of the step ----
+    float2 z[D], yv, fin;
+#pragma unroll
+    for (int c = 0; c < D; ++c) z[c] = zn[c];
+    yv = yn;
+    finish_pair<D>(z, yv, r < n, r + 1 < n, fin);
+    if (ROLLING) {
+      float2 lf;
+      finish_pair<D>(zln, yln, r - window >= 0 && r - window < n, r + 1 - window >= 0 && r + 1 - window < n, lf);
+      put_products<D, true>(tile, lane, z, yv, fin, zln, yln, lf);
+    } else {
+      put_products<D, false>(tile, lane, z, yv, fin, z, yv, fin);
+    }
+    load_pair<D>(X, ldx, y, p, r + SB, n, zn, yn);
+    if (ROLLING) load_pair<D>(X, ldx, y, p, r + SB - window, n, zln, yln);
+    __syncwarp();
+    // ---- moment lanes: publish the base, scan, advance the base ----
+    {
+      float tot[TPL];
+#pragma unroll
+      for (int m = 0; m < TPL; ++m) if (lane + 32 * m < NM) basef[lane + 32 * m] = (float)W[m];
+      scan_products<D>(tile, lane, tot);
+#pragma unroll
+      for (int m = 0; m < TPL; ++m) W[m] += (double)tot[m];
+    }
+    __syncwarp();
+    // ---- row lanes: W_t = base + scan(t), solve both rows, predict ----
+    float2 g[NM];
+    {
+      const float2* src = reinterpret_cast<const float2*>(tile) + lane;
+#pragma unroll
+      for (int c4 = 0; c4 < NB / 4; ++c4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(basef + 4 * c4);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = 4 * c4 + u;
+          if (c < NM) g[c] = __fadd2_rn(src[(size_t)c * (SBP / 2)], bc(bb[u]));
+        }
+      }
+    }
+    __syncwarp();
+    const float2 cn = g[NM - 1];
+    bool ok0, ok1;
+    if (ROLLING) {
+      ok0 = (r >= window - 1) && (!skip || cn.x >= (float)min_rows - 0.5f);
+      ok1 = (r + 1 >= window - 1) && (!skip || cn.y >= (float)min_rows - 0.5f);
+    } else {
+      ok0 = skip ? (fin.x != 0.0f && cn.x >= (float)min_rows - 0.5f) : (r + row0 >= min_rows - 1);
+      ok1 = skip ? (fin.y != 0.0f && cn.y >= (float)min_rows - 0.5f) : (r + 1 + row0 >= min_rows - 1);
+    }
+    float2 beta[D];
+    bool pd0, pd1;
+    chol_solve_pair<D>(g, lambda, beta, pd0, pd1);
+    float2 pr = bc(0.0f);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      beta[i] = f2(ok0 ? (pd0 ? beta[i].x : nanf("")) : 0.0f, ok1 ? (pd1 ? beta[i].y : nanf("")) : 0.0f);
+      pr = __ffma2_rn(z[i], beta[i], pr);
+    }
+    // rows 2l, 2l+1 are adjacent: 2 D consecutive floats per lane, consecutive lanes consecutive -> coalesced
+    if (r + 1 < n) {
+      float* cdst = coeffs + r * D;
+      if ((D & 1) == 0) {
+        float2* c2 = reinterpret_cast<float2*>(cdst);
+#pragma unroll
+        for (int i = 0; i < D / 2; ++i) c2[i] = f2(beta[2 * i].x, beta[2 * i + 1].x);
+#pragma unroll
+        for (int i = 0; i < D / 2; ++i) c2[D / 2 + i] = f2(beta[2 * i].y, beta[2 * i + 1].y);
+      } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) cdst[i] = beta[i].x;
+#pragma unroll
+        for (int i = 0; i < D; ++i) cdst[D + i] = beta[i].y;
+      }
+      pred[r] = pr.x; pred[r + 1] = pr.y;
+      valid[r] = ok0 ? 1 : 0; valid[r + 1] = ok1 ? 1 : 0;
+    } else if (r < n) {
+      float* cdst = coeffs + r * D;
+#pragma unroll
+      for (int i = 0; i < D; ++i) cdst[i] = beta[i].x;
+      pred[r] = pr.x;
+      valid[r] = ok0 ? 1 : 0;
+    }
+  }
+}
+
+// =====================================================================================================================
+// Generic pass C for any number of coefficients (D > 12): the reference takes any p (lr_online_solvers.rs:148-301).
+// One warp per chain, rows in order; the window moments live in shared memory as f64 ((D+2)(D+3)/2 packed upper
+// triangle over (z, y, 1)), lanes stride over the moments for the rank-1 updates and cooperate on an f64 Cholesky of a
+// scratch copy per row.  O(D^3 / 32) per row — a correctness path, not a roofline one.
+// =====================================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(32)
+online_generic_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y, int64_t n, int p, int d,
+                      int64_t window, int64_t min_rows, int skip, double lambda, int64_t row0, int64_t nchains,
+                      const double* __restrict__ C /* [NM][nchains] */, T* __restrict__ coeffs, T* __restrict__ pred,
+                      uint8_t* __restrict__ valid) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const int64_t k = blockIdx.x;
+  const int ng = d * (d + 1) / 2, nm = ng + d + 1;
+  double* W = reinterpret_cast<double*>(smem_raw);      // [nm] window moments, component order of the chain sums
+  double* A = W + nm;                                   // [d*d] scratch (lower triangle used)
+  double* e = A + d * d;                                // [d+2] entering row
+  double* l = e + d + 2;                                // [d+2] leaving row
+  double* bt = l + d + 2;                               // [d]
+  const bool rolling = window > 0;
+  const int64_t chain0 = k * CHAIN_ROWS;
+  auto load_row = [&](int64_t r, double* dst, bool use) {
+    bool fin = use && r >= 0 && r < n;
+    double acc = 0.0;
+    for (int c = lane; c <= d; c += 32) {
+      double v = 0.0;
+      if (fin) v = (c < p) ? (double)X[(size_t)c * ldx + r] : (c < d ? 1.0 : (double)y[r]);
+      dst[c] = v;
+      acc += v * 0.0;
+    }
+    for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    fin = fin && (acc == 0.0);
+    __syncwarp();
+    if (!fin) for (int c = lane; c <= d; c += 32) dst[c] = 0.0;
+    if (lane == 0) dst[d + 1] = fin ? 1.0 : 0.0;
+    __syncwarp();
+    return fin;
+  };
+  auto rank1 = [&](const double* v, double sgn) {       // W += sgn * m(v)
+    for (int c = lane; c < nm; c += 32) {
+      int i, j;
+      if (c >= ng + d) { i = j = d + 1; }
+      else if (c >= ng) { i = c - ng; j = d; }
+      else { int cc = c; i = 0; while (cc >= d - i) { cc -= d - i; ++i; } j = i + cc; }
+      W[c] += sgn * v[i] * v[j];
+    }
+    __syncwarp();
+  };
+  for (int c = lane; c < nm; c += 32) W[c] = C[(size_t)c * nchains + k];
+  __syncwarp();
+  if (rolling) {
+    const int64_t lo = max((int64_t)0, chain0 - window);
+    const int64_t kl = lo / CHAIN_ROWS;
+    for (int c = lane; c < nm; c += 32) W[c] -= C[(size_t)c * nchains + kl];
+    __syncwarp();
+    for (int64_t r = kl * CHAIN_ROWS; r < lo; ++r) { load_row(r, e, true); rank1(e, -1.0); }
+  }
+  for (int64_t r = chain0; r < min(chain0 + (int64_t)CHAIN_ROWS, n); ++r) {
+    const bool fin = load_row(r, e, true);
+    rank1(e, 1.0);
+    if (rolling) { load_row(r - window, l, true); rank1(l, -1.0); }
+    const double cn = W[nm - 1];
+    bool ok;
+    if (rolling) ok = (r >= window - 1) && (!skip || cn >= (double)min_rows - 0.5);
+    else ok = skip ? (fin && cn >= (double)min_rows - 0.5) : (r + row0 >= min_rows - 1);
+    bool pd = true;
+    if (ok) {
+      // A = lower triangle of G + lambda I, rounded through T like the packed kernels; bt = X'y
+      for (int c = lane; c < ng; c += 32) {
+        int cc = c, i = 0; while (cc >= d - i) { cc -= d - i; ++i; } const int j = i + cc;
+        A[j * d + i] = (double)(T)W[c] + (i == j ? lambda : 0.0);
+      }
+      for (int c = lane; c < d; c += 32) bt[c] = (double)(T)W[ng + c];
+      __syncwarp();
+      for (int c = 0; c < d; ++c) {
+        const double dg = A[c * d + c];
+        if (!(dg > 0.0) || !isfinite(dg)) pd = false;
+        const double inv = rsqrt(dg);
+        __syncwarp();
+        for (int i = c + 1 + lane; i < d; i += 32) A[i * d + c] *= inv;
+        if (lane == 0) A[c * d + c] = inv;
+        __syncwarp();
+        for (int idx = lane; idx < (d - c - 1) * (d - c - 1); idx += 32) {
+          const int j = c + 1 + idx / (d - c - 1), i = c + 1 + idx % (d - c - 1);
+          if (i >= j) A[i * d + j] -= A[i * d + c] * A[j * d + c];
+        }
+        __syncwarp();
+      }
+      for (int i = 0; i < d; ++i) {            // forward substitution (lane-parallel dot)
+        double s = 0.0;
+        for (int j = lane; j < i; j += 32) s += A[i * d + j] * bt[j];
+        for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) bt[i] = (bt[i] - s) * A[i * d + i];
+        __syncwarp();
+      }
+      for (int i = d - 1; i >= 0; --i) {       // backward
+        double s = 0.0;
+        for (int j = i + 1 + lane; j < d; j += 32) s += A[j * d + i] * bt[j];
+        for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) bt[i] = (bt[i] - s) * A[i * d + i];
+        __syncwarp();
+      }
+    }
+    double prs = 0.0;
+    for (int c = lane; c < d; c += 32) {
+      const double bv = ok ? (pd ? bt[c] : nan("")) : 0.0;
+      coeffs[r * d + c] = (T)bv;
+      const double zc = (c < p) ? (double)X[(size_t)c * ldx + r] : 1.0;
+      prs += ok ? zc * (double)(T)bv : 0.0;
+    }
+    for (int off = 16; off; off >>= 1) prs += __shfl_xor_sync(0xffffffffu, prs, off);
+    if (lane == 0) { pred[r] = (T)prs; valid[r] = ok ? 1 : 0; }
+    __syncwarp();
+  }
+}
+
+// chain sums for any d (generic path): one warp per chain, lanes stride over the moments
+template <typename T>
+__global__ void __launch_bounds__(32)
+chain_sums_generic_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y, int64_t n, int p, int d,
+                          int64_t nchains, double* __restrict__ S) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const int64_t k = blockIdx.x;
+  const int ng = d * (d + 1) / 2, nm = ng + d + 1;
+  double* acc = reinterpret_cast<double*>(smem_raw);   // [nm]
+  double* e = acc + nm;                                // [d+2]
+  for (int c = lane; c < nm; c += 32) acc[c] = 0.0;
+  __syncwarp();
+  for (int64_t r = k * CHAIN_ROWS; r < min((k + 1) * (int64_t)CHAIN_ROWS, n); ++r) {
+    double z0 = 0.0;
+    for (int c = lane; c <= d; c += 32) {
+      const double v = (c < p) ? (double)X[(size_t)c * ldx + r] : (c < d ? 1.0 : (double)y[r]);
+      e[c] = v; z0 += v * 0.0;
+    }
+    for (int off = 16; off; off >>= 1) z0 += __shfl_xor_sync(0xffffffffu, z0, off);
+    __syncwarp();
+    if (z0 == 0.0) {
+      if (lane == 0) e[d + 1] = 1.0;
+      __syncwarp();
+      for (int c = lane; c < nm; c += 32) {
+        int i, j;
+        if (c >= ng + d) { i = j = d + 1; }
+        else if (c >= ng) { i = c - ng; j = d; }
+        else { int cc = c; i = 0; while (cc >= d - i) { cc -= d - i; ++i; } j = i + cc; }
+        acc[c] += e[i] * e[j];
+      }
+    }
+    __syncwarp();
+  }
+  for (int c = lane; c < nm; c += 32) S[(size_t)c * nchains + k] = acc[c];
+}
+
+template <typename T>
+int run_online_generic(const T* X, int64_t ldx, const T* y, int64_t n, int p, int d, int64_t window, int64_t min_rows,
+                       int skip, double lambda, const double* m0, int64_t row0, T* coeffs, T* pred, uint8_t* valid,
+                       cudaStream_t s) {
+  const int nm = d * (d + 1) / 2 + d + 1;
+  const int64_t nchains = ceil_div(n, CHAIN_ROWS);
+  double* S = nullptr;
+  if (dev_alloc((void**)&S, (size_t)nm * nchains * sizeof(double), s)) return 1;
+  const size_t smem_a = (size_t)(nm + d + 2) * sizeof(double);
+  const size_t smem_c = (size_t)(nm + d * d + 2 * (d + 2) + d) * sizeof(double);
+  if (smem_c > 200 * 1024) { dev_free(S, s); set_error("rolling/recursive lin_reg: %d coefficients exceed the device limit (about 150)", d); return 1; }
+  auto ka = chain_sums_generic_kernel<T>;
+  auto kc = online_generic_kernel<T>;
+  if (smem_a > 48 * 1024) PDSB_CUDA_OK(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+  if (smem_c > 48 * 1024) PDSB_CUDA_OK(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+  ka<<<(unsigned)nchains, 32, smem_a, s>>>(X, ldx, y, n, p, d, nchains, S);
+  cudaError_t e = cudaGetLastError(); count_launch();
+  if (e == cudaSuccess) { tile_scan_kernel<<<nm, 1024, 0, s>>>(S, nchains, m0, p, d); e = cudaGetLastError(); count_launch(); }
+  if (e == cudaSuccess) {
+    kc<<<(unsigned)nchains, 32, smem_c, s>>>(X, ldx, y, n, p, d, window, min_rows, skip, lambda, row0, nchains, S, coeffs, pred, valid);
+    e = cudaGetLastError(); count_launch();
+  }
+  dev_free(S, s);
+  if (e != cudaSuccess) { set_error("online lin_reg (generic) launch failed: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+// packed f32 pass C (only meaningful for T = float)
+template <int D>
+int launch_main_f32x2(const float* X, int64_t ldx, const float* y, int64_t n, int p, int64_t window, int64_t min_rows,
+                      int skip, double lambda, int64_t row0, int64_t nchains, const double* S, float* coeffs, float* pred,
+                      uint8_t* valid, cudaStream_t s) {
+  const size_t smem = V2_WARPS * V2<D>::warp_floats * sizeof(float);
+  const unsigned grid = (unsigned)ceil_div(nchains, V2_WARPS);
+  if (window > 0) {
+    auto kc = online_main_f32x2_kernel<D, true>;
+    if (smem > 48 * 1024) PDSB_CUDA_OK(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kc<<<grid, V2_WARPS * 32, smem, s>>>(X, ldx, y, n, p, window, min_rows, skip, (float)lambda, row0, nchains, S, coeffs, pred, valid);
+  } else {
+    auto kc = online_main_f32x2_kernel<D, false>;
+    if (smem > 48 * 1024) PDSB_CUDA_OK(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kc<<<grid, V2_WARPS * 32, smem, s>>>(X, ldx, y, n, p, window, min_rows, skip, (float)lambda, row0, nchains, S, coeffs, pred, valid);
+  }
+  return 0;
+}
+template <typename T, int D> struct MainF32x2 {
+  static bool use() { return false; }
+  static int run(const T*, int64_t, const T*, int64_t, int, int64_t, int64_t, int, double, int64_t, int64_t, const double*, T*, T*, uint8_t*, cudaStream_t) { return 1; }
+};
+template <int D> struct MainF32x2<float, D> {
+  // D <= 9 keeps the packed kernel free of register spills (201 registers at D = 8, 236 at D = 9); wider fits use the
+  // lane-per-moment kernel above.  PDSB_ONLINE_V1=1 forces the old kernel (A/B timing).
+  static bool use() { static int v = [] { const char* e = getenv("PDSB_ONLINE_V1"); return e && atoi(e) ? 0 : 1; }(); return v != 0 && D <= 9; }
+  static int run(const float* X, int64_t ldx, const float* y, int64_t n, int p, int64_t window, int64_t min_rows, int skip,
+                 double lambda, int64_t row0, int64_t nchains, const double* S, float* coeffs, float* pred, uint8_t* valid,
+                 cudaStream_t s) {
+    return launch_main_f32x2<D>(X, ldx, y, n, p, window, min_rows, skip, lambda, row0, nchains, S, coeffs, pred, valid, s);
+  }
+};
+
 template <typename T, int D>
 int run_online(const T* X, int64_t ldx, const T* y, int64_t n, int p, int64_t window, int64_t min_rows, int skip,
                double lambda, const double* m0, int64_t row0, T* coeffs, T* pred, uint8_t* valid, cudaStream_t s) {
@@ -404,7 +906,11 @@ int run_online(const T* X, int64_t ldx, const T* y, int64_t n, int p, int64_t wi
   cudaError_t e = cudaGetLastError(); count_launch();
   if (e == cudaSuccess) { tile_scan_kernel<<<NM, 1024, 0, s>>>(S, nchains, m0, p, D); e = cudaGetLastError(); count_launch(); }
   if (e == cudaSuccess) {
-    kc<<<grid, CTA_THREADS, smem, s>>>(X, ldx, y, n, p, window, min_rows, skip, (T)lambda, row0, nchains, S, coeffs, pred, valid);
+    if (MainF32x2<T, D>::use()) {
+      if (MainF32x2<T, D>::run(X, ldx, y, n, p, window, min_rows, skip, lambda, row0, nchains, S, coeffs, pred, valid, s)) { dev_free(S, s); return 1; }
+    } else {
+      kc<<<grid, CTA_THREADS, smem, s>>>(X, ldx, y, n, p, window, min_rows, skip, (T)lambda, row0, nchains, S, coeffs, pred, valid);
+    }
     e = cudaGetLastError(); count_launch();
   }
   dev_free(S, s);
@@ -426,9 +932,8 @@ int online_lin_reg(const T* X, int64_t ldx, const T* y, int64_t n, int p, int ad
   switch (d) {
     CASE_D(1) CASE_D(2) CASE_D(3) CASE_D(4) CASE_D(5) CASE_D(6) CASE_D(7) CASE_D(8) CASE_D(9) CASE_D(10)
     CASE_D(11) CASE_D(12)
-    default:
-      set_error("rolling/recursive lin_reg: %d coefficients not supported on device (max 12)", d);
-      return 1;
+    default:   // any number of coefficients, like the reference (lr_online_solvers.rs:148-301): generic shared-memory path
+      return run_online_generic<T>(X, ldx, y, n, p, d, window, min_rows, skip, lambda, m0, row0, coeffs, pred, valid, s);
   }
 #undef CASE_D
 }

@@ -117,10 +117,14 @@ def test_report_vs_oracle(monkeypatch, f64):
 
 @pytest.mark.parametrize("f64", [True, False])
 @pytest.mark.parametrize("window,p,bias,l2,n", [(1024, 8, False, 0.0, 0), (37, 3, True, 0.1, 0), (2, 1, False, 0.0, 0),
-                                                (5000, 4, True, 0.0, 0), (1024, 8, False, 0.0, 1_000_000)])
+                                                (5000, 4, True, 0.0, 0), (1024, 8, False, 0.0, 1_000_000),
+                                                (1024, 8, True, 0.0, 0), (100, 11, True, 0.0, 0), (64, 14, True, 0.05, 0),
+                                                (300, 30, False, 0.0, 0)])
 def test_rolling_vs_definition(monkeypatch, f64, window, p, bias, l2, n):
     """config[3] (window 1024, 8 features) up to 1e6 rows through the plugin ABI: every checked row == OLS on its window
-    (the identity the reference's tests assert, test_linear_exprs.py:814-854), >= 1000 rows checked at 1e6."""
+    (the identity the reference's tests assert, test_linear_exprs.py:814-854), >= 1000 rows checked at 1e6.  Coefficient
+    counts 1..9 take the packed f32 kernel (f32) / the lane-per-moment kernel (f64), 10..12 the lane-per-moment kernel,
+    above 12 the generic shared-memory path (the reference has no limit, lr_online_solvers.rs:148-301)."""
     monkeypatch.setattr(cfg, "LIN_REG_EXPR_F64", f64)
     n = n or max(3 * window + 77, 4000)
     df, xs = _frame(40 + p, n, p, np.float64 if f64 else np.float32)
