@@ -628,7 +628,7 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < RING; ++i) { mbar_init(&bars->raw_full[i], 1); mbar_init(&bars->raw_empty[i], 1); }
-    for (int i = 0; i < XAB; ++i) { mbar_init(&bars->a_full[i], nquad); mbar_init(&bars->a_empty[i], 1); }
+    for (int i = 0; i < XAB; ++i) { mbar_init(&bars->a_full[i], nquad + (nquad == 2 ? 1 : 0)); mbar_init(&bars->a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->d_full[i], 1); mbar_init(&bars->d_empty[i], nquad * EPI_SETS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -701,13 +701,19 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
       if (++fl == FLUSH_STAGES) { fl = 0; if (buf) dph ^= 1; buf ^= 1; }
     }
   } else if (warp < 2 + 4 * NCONV) {
-    // ---------------- converters: set j owns stages it = j (mod NCONV); only quadrants < nquad work ----------------
+    // ---------------- converters: set j owns stages it = j (mod NCONV) ----------------
+    // p <= 32: quadrant 0 = hi(X), quadrant 1 = lo(X), and the otherwise idle quadrant-2 warp of the set does the y / ones
+    // side work (lo(y) rows and the ones row of the B tile, sum y, sum y^2, y_i.y_j, row count), so no warp carries both a
+    // full LDS + STTM stream and the side work.  p > 32: quadrants 0..3 = hi/lo of two feature groups, quadrant 0 also
+    // does the side work.
     const int quad = warp & 3;
     const uint32_t set = (uint32_t)(warp - 2) >> 2;
-    if (quad < nquad) {
+    const bool do_x = quad < nquad;
+    const bool do_y = (nquad == 2) ? (quad == 2) : (quad == 0);
+    if (do_x || do_y) {
       const bool is_lo = quad & 1;
       const int m = (quad >> 1) * 32 + lane;             // feature column
-      const bool is_data = m < p;
+      const bool is_data = do_x && m < p;
       const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
       const int xrow = zx + m;
       const uint32_t sw = (uint32_t)(xrow & 7);
@@ -738,7 +744,7 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] = 0u;
           }
-          if (quad == 0) {          // warp-uniform
+          if (do_y) {               // warp-uniform
             // 8 lanes per target: lane 8j + c handles the c-th 16-byte chunk of y_j's row (lo(y) row, sum y, sum y^2)
             if (lane < 8 * t) {
               const int j = lane >> 3, c = lane & 7;
@@ -785,18 +791,18 @@ gram_tcgen05_xonly_kernel(const __grid_constant__ CUtensorMap tmap, const float*
               v[k] = __float_as_uint(x - __uint_as_float(v[k] & 0xFFFFE000u));
             }
           }
-          tmem_st32(tmem + lane_addr + (uint32_t)(XA_COL0 + s * A_SLOT_COLS + b * BOX_ROWS), v);
+          if (do_x) tmem_st32(tmem + lane_addr + (uint32_t)(XA_COL0 + s * A_SLOT_COLS + b * BOX_ROWS), v);
         }
         dsy += (double)sy; dsyy += (double)syy; sy = 0.0f; syy = 0.0f;
 #pragma unroll
         for (int d = 0; d < 3; ++d) { dxy[d] += (double)sxy[d]; sxy[d] = 0.0f; }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        if (quad == 0) fence_async_smem();    // lo(y) / ones rows written through the generic proxy
+        if (do_y) fence_async_smem();         // lo(y) / ones rows written through the generic proxy
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->a_full[s]);
       }
-      if (quad == 0) {
+      if (do_y) {
         // reduce the 8 chunk-lanes of every target (fixed order -> reproducible) and the masked-row count
         double* ys = yside + ((size_t)blockIdx.x * NCONV + set) * YSIDE_STRIDE;
         for (int off = 4; off; off >>= 1) {

@@ -906,7 +906,10 @@ int run_online(const T* X, int64_t ldx, const T* y, int64_t n, int p, int64_t wi
   cudaError_t e = cudaGetLastError(); count_launch();
   if (e == cudaSuccess) { tile_scan_kernel<<<NM, 1024, 0, s>>>(S, nchains, m0, p, D); e = cudaGetLastError(); count_launch(); }
   if (e == cudaSuccess) {
-    if (MainF32x2<T, D>::use()) {
+    // The packed kernel sums a step's products in f32 from zero: for a window shorter than the 64-row step the partial sums
+    // (a random walk over 64 rows) are larger than the window sum they end in and the rounding shows (3e-6 relative at
+    // window 2); such windows keep the f64 lane-per-moment walk.  Recursive fits and windows >= 64 take the packed kernel.
+    if (MainF32x2<T, D>::use() && (window == 0 || window >= SB)) {
       if (MainF32x2<T, D>::run(X, ldx, y, n, p, window, min_rows, skip, lambda, row0, nchains, S, coeffs, pred, valid, s)) { dev_free(S, s); return 1; }
     } else {
       kc<<<grid, CTA_THREADS, smem, s>>>(X, ldx, y, n, p, window, min_rows, skip, (T)lambda, row0, nchains, S, coeffs, pred, valid);
