@@ -261,6 +261,146 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, const double* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Staged variant (the production f64 path for n >= 4096 rows): the direct kernel above loads one 8-byte scalar per lane
+// and 4-row step, i.e. eight 32-byte sectors of eight different columns per load instruction, with 4 rows in flight per
+// warp — 33 % of the HBM peak at 33 columns (round 1).  Here every CTA streams 128-row tiles: one elected thread issues a
+// 1-D bulk async copy (cp.async.bulk, the TMA engine) per column — 1 KiB contiguous each — into a shared-memory tile
+// [column][132] (pitch 132 doubles: the 8-column x 4-row fragment read of a warp is bank-conflict-free), completion on an
+// mbarrier ring of STAGES tiles.  Warps take 16 rows of a tile each: per 4-row step NB LDS.64 feed the same
+// NB (NB + 1) / 2 DMMAs as before.  Rows in flight per CTA: STAGES x 128.  Only whole 128-row tiles are handled here; the
+// tail (< 128 rows) goes through the direct kernel into further partials, and a fixed-order reduce joins both.
+constexpr int DT_R = 128;                 // rows per tile
+constexpr int DT_RP = 132;                // pitch in doubles (132 * 8 B = 32 B mod 128 B)
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int NB>
+__global__ void __launch_bounds__(256)
+gram_dmma_staged_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
+                        const double* __restrict__ w, const double* __restrict__ mask, int64_t ntiles, int p, int t,
+                        int stages, double* __restrict__ partials /* [grid][q1*q1] */) {
+  constexpr int NP = NB * (NB + 1) / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ncol = p + t + (w ? 1 : 0) + (mask ? 1 : 0);       // staged columns: data, then weights, then mask
+  const int wcol = p + t, mcol = p + t + (w ? 1 : 0);
+  const size_t tile_doubles = (size_t)ncol * DT_RP;
+  double* tiles = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)stages * tile_doubles);
+  uint64_t* empty = full + stages;
+  double* sm = tiles;                                          // reused for the CTA reduction after the main loop
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, k = lane & 3;
+  const int q1 = p + t + 1;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(&full[i])), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(&empty[i])), "r"(8));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t my_tiles = ntiles > (int64_t)blockIdx.x ? (uint32_t)((ntiles - 1 - blockIdx.x) / gridDim.x + 1) : 0u;
+  auto issue = [&](uint32_t it) {      // one thread: all columns of tile `it` of this CTA -> stage it % stages
+    const int st = it % stages;
+    const int64_t r0 = ((int64_t)it * gridDim.x + blockIdx.x) * DT_R;
+    const uint32_t bar = smem_addr_u32(&full[st]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(ncol * DT_R * 8)) : "memory");
+    double* dst = tiles + (size_t)st * tile_doubles;
+    for (int c = 0; c < ncol; ++c) {
+      const double* src = c < p ? X + (int64_t)c * ldx + r0 : (c < p + t ? Y + (int64_t)(c - p) * ldy + r0 : ((w && c == wcol) ? w + r0 : mask + r0));
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_addr_u32(dst + (size_t)c * DT_RP)), "l"(src), "r"((uint32_t)(DT_R * 8)), "r"(bar) : "memory");
+    }
+  };
+  auto wait = [&](uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+      asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                   : "=r"(done) : "r"(smem_addr_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+      if (!done && spins > (1u << 24)) __trap();
+    }
+  };
+  if (threadIdx.x == 0)
+    for (uint32_t it = 0; it < my_tiles && it < (uint32_t)stages; ++it) issue(it);
+
+  int kind[NB], cidx[NB];                 // 0 data column cidx, 1 ones / mask, 2 zero padding
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int c = 8 * b + g;
+    kind[b] = c < p + t ? 0 : (c == p + t ? 1 : 2);
+    cidx[b] = c < p + t ? c : 0;
+  }
+  double acc[NP][2];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+
+  for (uint32_t it = 0; it < my_tiles; ++it) {
+    const int st = it % stages;
+    const uint32_t ph = (it / stages) & 1;
+    wait(&full[st], ph);
+    const double* tile = tiles + (size_t)st * tile_doubles;
+#pragma unroll
+    for (int step = 0; step < 4; ++step) {
+      const int r = warp * 16 + step * 4 + k;
+      double z[NB];
+      const double mk = mask ? tile[(size_t)mcol * DT_RP + r] : 1.0;
+      const double wv = w ? tile[(size_t)wcol * DT_RP + r] : 1.0;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) z[b] = kind[b] == 0 ? tile[(size_t)cidx[b] * DT_RP + r] : (kind[b] == 1 ? mk : 0.0);
+      int idx = 0;
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        const double a = z[i] * wv;
+#pragma unroll
+        for (int j = i; j < NB; ++j) { dmma884(acc[idx][0], acc[idx][1], a, z[j]); ++idx; }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(&empty[st])) : "memory");
+    if (threadIdx.x == 0 && it + stages < my_tiles) {     // refill this stage once all 8 warps have left it
+      wait(&empty[st], ph);
+      issue(it + stages);
+    }
+  }
+  __syncthreads();       // every tile consumed: the tile memory becomes the reduction scratch
+  for (int wturn = 0; wturn < 8; ++wturn) {
+    if (warp == wturn) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        double* d = sm + i * 64 + g * 8 + 2 * k;
+        if (wturn == 0) { d[0] = acc[i][0]; d[1] = acc[i][1]; }
+        else { d[0] += acc[i][0]; d[1] += acc[i][1]; }
+      }
+    }
+    __syncthreads();
+  }
+  double* out = partials + (size_t)blockIdx.x * q1 * q1;
+  for (int e = threadIdx.x; e < NP * 64; e += 256) {
+    const int blk = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+    int i = 0, rem = blk;
+    while (rem >= NB - i) { rem -= NB - i; ++i; }
+    const int j = i + rem;
+    const int a = 8 * i + rr, b = 8 * j + cc;
+    if (a < q1 && b < q1 && (i != j || a <= b)) {
+      const double v = sm[e];
+      out[(size_t)a * q1 + b] = v;
+      out[(size_t)b * q1 + a] = v;
+    }
+  }
+}
+
+template <int NB>
+static int launch_dmma_staged(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w, const double* mask,
+                              int64_t ntiles, int p, int t, int grid, int stages, size_t smem, double* partials, cudaStream_t s) {
+  auto k = gram_dmma_staged_kernel<NB>;
+  PDSB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, 256, smem, s>>>(X, ldx, Y, ldy, w, mask, ntiles, p, t, stages, partials);
+  PDSB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
 template <int NB>
 static int launch_dmma(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w, const double* mask,
                        int64_t n, int p, int t, int grid, double* partials, cudaStream_t s) {
@@ -278,22 +418,56 @@ static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64
   const int q1 = p + t + 1;
   const int nb = (q1 + 7) / 8;
   if (!enabled || nb < 1 || nb > 8 || n < 1) return -1;
-  int grid = (int)std::min<int64_t>(ceil_div(n, 32), (int64_t)sm_count() * 4);
-  if (grid < 1) grid = 1;
-  double* partials = nullptr;
-  if (dev_alloc((void**)&partials, (size_t)grid * q1 * q1 * sizeof(double), s)) return 1;
-  int rc;
-  switch (nb) {
-    case 1: rc = launch_dmma<1>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
-    case 2: rc = launch_dmma<2>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
-    case 3: rc = launch_dmma<3>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
-    case 4: rc = launch_dmma<4>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
-    case 5: rc = launch_dmma<5>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
-    case 6: rc = launch_dmma<6>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
-    case 7: rc = launch_dmma<7>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
-    default: rc = launch_dmma<8>(X, ldx, Y, ldy, w, mask, n, p, t, grid, partials, s); break;
+  // staged kernel for the whole 128-row tiles (needs 16-byte aligned columns), direct kernel for the rest
+  static const bool staged_on = [] { const char* e = getenv("PDSB_K2A_STAGED"); return !(e && e[0] == '0'); }();
+  const int ncol = p + t + (w ? 1 : 0) + (mask ? 1 : 0);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool aligned = al16(X) && al16(Y) && (ldx % 2 == 0) && (ldy % 2 == 0) && (!w || al16(w)) && (!mask || al16(mask));
+  const size_t tile_bytes = (size_t)ncol * DT_RP * sizeof(double);
+  int stages = (int)std::min<size_t>(4, (200 * 1024 - 256) / tile_bytes);
+  const size_t red_bytes = (size_t)(nb * (nb + 1) / 2) * 64 * sizeof(double);
+  const int64_t ntiles = (staged_on && aligned && stages >= 2 && n >= 4096) ? n / DT_R : 0;
+  const int64_t n_main = ntiles * DT_R;
+  const int64_t n_tail = n - n_main;
+  int grid_main = 0, grid = 0;
+  if (ntiles > 0) {
+    // one or two CTAs per SM, whatever shared memory allows
+    const size_t smem_need = std::max((size_t)stages * tile_bytes, red_bytes) + 2 * stages * sizeof(uint64_t) + 128;
+    const int per_sm = smem_need <= 100 * 1024 ? 2 : 1;
+    grid_main = (int)std::min<int64_t>(ntiles, (int64_t)sm_count() * per_sm);
   }
-  if (rc) { dev_free(partials, s); return rc; }
+  if (n_tail > 0) grid = (int)std::min<int64_t>(ceil_div(n_tail, 32), (int64_t)sm_count() * 4);
+  if (grid_main + grid < 1) grid = 1;
+  double* partials = nullptr;
+  if (dev_alloc((void**)&partials, (size_t)(grid_main + grid) * q1 * q1 * sizeof(double), s)) return 1;
+  int rc = 0;
+  if (grid_main > 0) {
+    const size_t smem = std::max((size_t)stages * tile_bytes, red_bytes) + 2 * stages * sizeof(uint64_t) + 128;
+#define PDSB_ST(NBV) rc = launch_dmma_staged<NBV>(X, ldx, Y, ldy, w, mask, ntiles, p, t, grid_main, stages, smem, partials, s)
+    switch (nb) {
+      case 1: PDSB_ST(1); break; case 2: PDSB_ST(2); break; case 3: PDSB_ST(3); break; case 4: PDSB_ST(4); break;
+      case 5: PDSB_ST(5); break; case 6: PDSB_ST(6); break; case 7: PDSB_ST(7); break; default: PDSB_ST(8); break;
+    }
+#undef PDSB_ST
+    if (rc) { dev_free(partials, s); return rc; }
+  }
+  if (grid > 0) {
+    const double* Xt = X + n_main; const double* Yt = Y + n_main;
+    const double* wt = w ? w + n_main : nullptr; const double* mt = mask ? mask + n_main : nullptr;
+    double* pt = partials + (size_t)grid_main * q1 * q1;
+    switch (nb) {
+      case 1: rc = launch_dmma<1>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+      case 2: rc = launch_dmma<2>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+      case 3: rc = launch_dmma<3>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+      case 4: rc = launch_dmma<4>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+      case 5: rc = launch_dmma<5>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+      case 6: rc = launch_dmma<6>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+      case 7: rc = launch_dmma<7>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+      default: rc = launch_dmma<8>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+    }
+    if (rc) { dev_free(partials, s); return rc; }
+  }
+  grid += grid_main;
   const int len = q1 * q1;
   reduce_partials_kernel<<<len, 128, 0, s>>>(partials, grid, len, M);
   cudaError_t e = cudaGetLastError();

@@ -167,27 +167,40 @@ chain_sums_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y,
 #pragma unroll
   for (int c = 0; c < NM; ++c) v[c] = 0.0;
   const int64_t chain0 = k * CHAIN_ROWS;
-#pragma unroll 2
-  for (int j = 0; j < CHAIN_ROWS / 32; ++j) {
-    const int64_t r = chain0 + (int64_t)j * 32 + lane;
-    T z[D]; T yv;
-    load_raw<T, D>(X, ldx, y, p, r, n, z, yv);
-    T acc = yv * T(0);
+  // The pass is a pure stream (read (p+1) s bytes per row, keep NM sums): what bounds it is bytes in flight.  ncu, round
+  // 2: with one 32-row batch of loads per warp outstanding the kernel sat at 25 % of the HBM peak (2.1 ms per 1e8 x 9
+  // f32).  PF batches are kept in flight per warp (register ring, statically indexed by unrolling the loop PF times).
+  constexpr int PF = (D <= 6 || (sizeof(T) == 4 && D <= 9)) ? 4 : 2;
+  T zb[PF][D]; T yb[PF];
 #pragma unroll
-    for (int c = 0; c < D; ++c) acc = fma(z[c], T(0), acc);
-    const bool fin = (r < n) && (acc == T(0));
-    double dz[D];
+  for (int u = 0; u < PF; ++u) load_raw<T, D>(X, ldx, y, p, chain0 + (int64_t)u * 32 + lane, n, zb[u], yb[u]);
+  for (int j0 = 0; j0 < CHAIN_ROWS / 32; j0 += PF) {
 #pragma unroll
-    for (int c = 0; c < D; ++c) dz[c] = fin ? (double)z[c] : 0.0;
-    const double dy = fin ? (double)yv : 0.0;
-    int q = 0;
+    for (int u = 0; u < PF; ++u) {
+      const int j = j0 + u;
+      const int64_t r = chain0 + (int64_t)j * 32 + lane;
+      T z[D]; T yv;
 #pragma unroll
-    for (int i = 0; i < D; ++i)
+      for (int c = 0; c < D; ++c) z[c] = zb[u][c];
+      yv = yb[u];
+      if (j + PF < CHAIN_ROWS / 32) load_raw<T, D>(X, ldx, y, p, r + PF * 32, n, zb[u], yb[u]);
+      T acc = yv * T(0);
 #pragma unroll
-      for (int jj = i; jj < D; ++jj) { v[q] = fma(dz[i], dz[jj], v[q]); ++q; }
+      for (int c = 0; c < D; ++c) acc = fma(z[c], T(0), acc);
+      const bool fin = (r < n) && (acc == T(0));
+      double dz[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) { v[q] = fma(dz[i], dy, v[q]); ++q; }
-    v[q] += fin ? 1.0 : 0.0;
+      for (int c = 0; c < D; ++c) dz[c] = fin ? (double)z[c] : 0.0;
+      const double dy = fin ? (double)yv : 0.0;
+      int q = 0;
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int jj = i; jj < D; ++jj) { v[q] = fma(dz[i], dz[jj], v[q]); ++q; }
+#pragma unroll
+      for (int i = 0; i < D; ++i) { v[q] = fma(dz[i], dy, v[q]); ++q; }
+      v[q] += fin ? 1.0 : 0.0;
+    }
   }
 #pragma unroll
   for (int c = 0; c < NM; ++c) {
@@ -409,6 +422,7 @@ online_main_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y
 constexpr int SB = 64;                   // rows per step of the packed kernel
 constexpr int SBP = 68;                  // row stride of the product tile: 272 B = 16 (mod 128) -> conflict-free LDS.128 scans
 constexpr int V2_WARPS = 4;
+constexpr int K6_DEFAULT_VAR = 0;         // see online_main_f32x2_kernel (PDSB_K6_VAR overrides for A/B timing)
 
 template <int D> struct V2 {
   static constexpr int NG = D * (D + 1) / 2;
@@ -422,10 +436,10 @@ __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b
 __device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
 
 // raw pair load (rows r, r+1; clamped addresses, no branches); z[D] (features, ones for the bias slot) and y
-template <int D>
+template <int D, bool CLAMP = true>
 __device__ __forceinline__ void load_pair(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, int p,
                                           int64_t r, int64_t n, float2* z, float2& yv) {
-  const int64_t r0 = min(max(r, (int64_t)0), n - 1), r1 = min(max(r + 1, (int64_t)0), n - 1);
+  const int64_t r0 = CLAMP ? min(max(r, (int64_t)0), n - 1) : r, r1 = CLAMP ? min(max(r + 1, (int64_t)0), n - 1) : r + 1;
   const float* q = X;
 #pragma unroll
   for (int c = 0; c < D; ++c) {
@@ -443,6 +457,7 @@ __device__ __forceinline__ void finish_pair(float2* z, float2& yv, bool in0, boo
   for (int c = 0; c < D; ++c) acc = __ffma2_rn(z[c], bc(0.0f), acc);      // 0 when every entry is finite, NaN otherwise
   const bool k0 = in0 && (acc.x == 0.0f), k1 = in1 && (acc.y == 0.0f);
   fin = f2(k0 ? 1.0f : 0.0f, k1 ? 1.0f : 0.0f);
+  if (__all_sync(0xffffffffu, k0 && k1)) return;             // the usual case: every row of the step exists and is finite
 #pragma unroll
   for (int c = 0; c < D; ++c) z[c] = f2(k0 ? z[c].x : 0.0f, k1 ? z[c].y : 0.0f);
   yv = f2(k0 ? yv.x : 0.0f, k1 ? yv.y : 0.0f);
@@ -524,24 +539,29 @@ __device__ __forceinline__ void chol_solve_pair(float2* g, float lambda, float2*
       for (int i = j; i < D; ++i) g[gidx<D>(i, j)] = __ffma2_rn(g[gidx<D>(i, c)], nj, g[gidx<D>(i, j)]);
     }
   }
+  float2 nb[D];                       // -beta: the packed FMA has no negate modifier, so the sign is carried by the vector
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     float2 s = beta[i];
 #pragma unroll
-    for (int j = 0; j < i; ++j) s = __ffma2_rn(__fmul2_rn(g[gidx<D>(i, j)], bc(-1.0f)), beta[j], s);
+    for (int j = 0; j < i; ++j) s = __ffma2_rn(g[gidx<D>(i, j)], nb[j], s);
     beta[i] = __fmul2_rn(s, g[gidx<D>(i, i)]);
+    nb[i] = __fmul2_rn(beta[i], bc(-1.0f));
   }
 #pragma unroll
   for (int i = D - 1; i >= 0; --i) {
     float2 s = beta[i];
 #pragma unroll
-    for (int j = i + 1; j < D; ++j) s = __ffma2_rn(__fmul2_rn(g[gidx<D>(j, i)], bc(-1.0f)), beta[j], s);
+    for (int j = i + 1; j < D; ++j) s = __ffma2_rn(g[gidx<D>(j, i)], nb[j], s);
     beta[i] = __fmul2_rn(s, g[gidx<D>(i, i)]);
+    nb[i] = __fmul2_rn(beta[i], bc(-1.0f));
   }
 }
 
-template <int D, bool ROLLING>
-__global__ void __launch_bounds__(V2_WARPS * 32)
+// VAR: 0 = register prefetch of the next step's rows (4-warp CTAs, 2 CTAs per SM at D = 8);
+//      1 / 2 = no register prefetch and a register cap for 3 / 4 CTAs per SM (more warps hide the load latency instead)
+template <int D, bool ROLLING, int VAR>
+__global__ void __launch_bounds__(V2_WARPS * 32, VAR == 0 ? 1 : (VAR == 1 ? 3 : 4))
 online_main_f32x2_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, int64_t n, int p,
                          int64_t window, int64_t min_rows, int skip, float lambda, int64_t row0, int64_t nchains,
                          const double* __restrict__ C /* [NM][nchains] exclusive chain prefixes */,
@@ -580,29 +600,49 @@ online_main_f32x2_kernel(const float* __restrict__ X, int64_t ldx, const float* 
     }
   }
 
-  // software pipeline: the raw rows of step b+1 are in flight while step b is scanned and solved
-  float2 zn[D], yn, zln[D], yln;
-  load_pair<D>(X, ldx, y, p, chain0 + 2 * lane, n, zn, yn);
-  if (ROLLING) load_pair<D>(X, ldx, y, p, chain0 + 2 * lane - window, n, zln, yln);
+  // interior chains (all but the first and the last few) need neither clamped addresses nor row-exists tests
+  const bool interior = (chain0 + CHAIN_ROWS + SB <= n) && (!ROLLING || chain0 - window >= 0);
+  constexpr bool PREF = (VAR == 0);
+  // VAR 0: software pipeline — the raw rows of step b+1 are in flight while step b is scanned and solved
+  float2 zn[PREF ? D : 1], yn, zln[PREF ? D : 1], yln;
+  if (PREF) {
+    load_pair<D>(X, ldx, y, p, chain0 + 2 * lane, n, zn, yn);
+    if (ROLLING) load_pair<D>(X, ldx, y, p, chain0 + 2 * lane - window, n, zln, yln);
+  }
   for (int b = 0; b < CHAIN_ROWS / SB; ++b) {
     const int64_t rb = chain0 + (int64_t)b * SB;
     if (rb >= n) break;
     const int64_t r = rb + 2 * lane;
     // ---- row lanes: products of the step ----
-    float2 z[D], yv, fin;
+    float2 z[D], yv, fin, zl[D], yl;
+    if (PREF) {
 #pragma unroll
-    for (int c = 0; c < D; ++c) z[c] = zn[c];
-    yv = yn;
-    finish_pair<D>(z, yv, r < n, r + 1 < n, fin);
+      for (int c = 0; c < D; ++c) { z[c] = zn[c]; if (ROLLING) zl[c] = zln[c]; }
+      yv = yn; yl = yln;
+    } else if (interior) {
+      load_pair<D, false>(X, ldx, y, p, r, n, z, yv);
+      if (ROLLING) load_pair<D, false>(X, ldx, y, p, r - window, n, zl, yl);
+    } else {
+      load_pair<D>(X, ldx, y, p, r, n, z, yv);
+      if (ROLLING) load_pair<D>(X, ldx, y, p, r - window, n, zl, yl);
+    }
+    finish_pair<D>(z, yv, interior || r < n, interior || r + 1 < n, fin);
     if (ROLLING) {
       float2 lf;
-      finish_pair<D>(zln, yln, r - window >= 0 && r - window < n, r + 1 - window >= 0 && r + 1 - window < n, lf);
-      put_products<D, true>(tile, lane, z, yv, fin, zln, yln, lf);
+      finish_pair<D>(zl, yl, interior || (r - window >= 0 && r - window < n), interior || (r + 1 - window >= 0 && r + 1 - window < n), lf);
+      put_products<D, true>(tile, lane, z, yv, fin, zl, yl, lf);
     } else {
       put_products<D, false>(tile, lane, z, yv, fin, z, yv, fin);
     }
-    load_pair<D>(X, ldx, y, p, r + SB, n, zn, yn);
-    if (ROLLING) load_pair<D>(X, ldx, y, p, r + SB - window, n, zln, yln);
+    if (PREF) {
+      if (interior) {
+        load_pair<D, false>(X, ldx, y, p, r + SB, n, zn, yn);
+        if (ROLLING) load_pair<D, false>(X, ldx, y, p, r + SB - window, n, zln, yln);
+      } else {
+        load_pair<D>(X, ldx, y, p, r + SB, n, zn, yn);
+        if (ROLLING) load_pair<D>(X, ldx, y, p, r + SB - window, n, zln, yln);
+      }
+    }
     __syncwarp();
     // ---- moment lanes: publish the base, scan, advance the base ----
     {
@@ -858,22 +898,32 @@ int run_online_generic(const T* X, int64_t ldx, const T* y, int64_t n, int p, in
 }
 
 // packed f32 pass C (only meaningful for T = float)
+template <int D, bool ROLLING, int VAR>
+int launch_main_f32x2_v(const float* X, int64_t ldx, const float* y, int64_t n, int p, int64_t window, int64_t min_rows,
+                        int skip, double lambda, int64_t row0, int64_t nchains, const double* S, float* coeffs, float* pred,
+                        uint8_t* valid, cudaStream_t s) {
+  const size_t smem = V2_WARPS * V2<D>::warp_floats * sizeof(float);
+  const unsigned grid = (unsigned)ceil_div(nchains, V2_WARPS);
+  auto kc = online_main_f32x2_kernel<D, ROLLING, VAR>;
+  if (smem > 48 * 1024) PDSB_CUDA_OK(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kc<<<grid, V2_WARPS * 32, smem, s>>>(X, ldx, y, n, p, window, min_rows, skip, (float)lambda, row0, nchains, S, coeffs, pred, valid);
+  return 0;
+}
+inline int k6_variant() {
+  static int v = [] { const char* e = getenv("PDSB_K6_VAR"); int x = e ? atoi(e) : K6_DEFAULT_VAR; return (x >= 0 && x <= 2) ? x : K6_DEFAULT_VAR; }();
+  return v;
+}
 template <int D>
 int launch_main_f32x2(const float* X, int64_t ldx, const float* y, int64_t n, int p, int64_t window, int64_t min_rows,
                       int skip, double lambda, int64_t row0, int64_t nchains, const double* S, float* coeffs, float* pred,
                       uint8_t* valid, cudaStream_t s) {
-  const size_t smem = V2_WARPS * V2<D>::warp_floats * sizeof(float);
-  const unsigned grid = (unsigned)ceil_div(nchains, V2_WARPS);
-  if (window > 0) {
-    auto kc = online_main_f32x2_kernel<D, true>;
-    if (smem > 48 * 1024) PDSB_CUDA_OK(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kc<<<grid, V2_WARPS * 32, smem, s>>>(X, ldx, y, n, p, window, min_rows, skip, (float)lambda, row0, nchains, S, coeffs, pred, valid);
-  } else {
-    auto kc = online_main_f32x2_kernel<D, false>;
-    if (smem > 48 * 1024) PDSB_CUDA_OK(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kc<<<grid, V2_WARPS * 32, smem, s>>>(X, ldx, y, n, p, window, min_rows, skip, (float)lambda, row0, nchains, S, coeffs, pred, valid);
-  }
-  return 0;
+#define PDSB_K6_GO(R, V) return launch_main_f32x2_v<D, R, V>(X, ldx, y, n, p, window, min_rows, skip, lambda, row0, nchains, S, coeffs, pred, valid, s)
+  const int var = k6_variant();
+  if (window > 0) { if (var == 1) PDSB_K6_GO(true, 1); if (var == 2) PDSB_K6_GO(true, 2); PDSB_K6_GO(true, 0); }
+  if (var == 1) PDSB_K6_GO(false, 1);
+  if (var == 2) PDSB_K6_GO(false, 2);
+  PDSB_K6_GO(false, 0);
+#undef PDSB_K6_GO
 }
 template <typename T, int D> struct MainF32x2 {
   static bool use() { return false; }

@@ -149,7 +149,7 @@ def test_rolling_vs_definition(monkeypatch, f64, window, p, bias, l2, n):
             for i in range(window - 1, m):
                 e32.setdefault(s0 + i, o["coeffs"][i])
         pool = np.array(sorted(e32))
-        rows = set(pool[rng.integers(0, len(pool), 1200 if n >= 1_000_000 else 60)].tolist()) | {window - 1, min(n - 1, 2 * window)}
+        rows = set(pool[rng.integers(0, len(pool), 1500 if n >= 1_000_000 else 60)].tolist()) | ({window - 1, min(n - 1, 2 * window)} & set(e32))
     else:
         rows = set(rng.integers(window - 1, n, 60).tolist()) | {window - 1, n - 1, window, min(n - 1, 2 * window)}
     for j in sorted(rows):
