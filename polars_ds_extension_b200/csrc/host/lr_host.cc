@@ -615,8 +615,21 @@ int host_grouped_t(const pdsb_column* cols, int n_cols, const int64_t* offsets, 
   const int q = F.p + add_bias;
   pdsb_solve_opts o{};
   o.p = F.p; o.t = 1; o.add_bias = add_bias; o.method = PDSB_METHOD_LSTSQ; o.solver = solver_from_string(kw->solver);
-  o.l2_reg = kw->l2_reg; o.singular_x_tol = kw->singular_x_tol;
-  if (kw->l1_reg > 0.0 || kw->positive) { set_error("grouped lin_reg: only OLS / ridge is batched"); return 1; }
+  o.l1_reg = kw->l1_reg; o.l2_reg = kw->l2_reg; o.tol = kw->tol; o.singular_x_tol = kw->singular_x_tol;
+  o.positive = kw->positive; o.max_iter = (int)kw->max_iter;
+  {   // the dispatch of pl_lr per group (linear_regression.rs:436-498), batched: OLS / ridge (gated), lasso / elastic net /
+      // positive ridge (coordinate descent), NNLS; the f32 twin's hard-coded iteration counts (_f32.rs:343,351,362)
+    const bool l1 = kw->l1_reg > 0.0, l2 = kw->l2_reg > 0.0;
+    const bool is_f32 = sizeof(T) == 4;
+    if (kw->weighted) { set_error("grouped lin_reg: weighted fits are not batched"); return 1; }
+    if (!l1 && !kw->positive) o.method = PDSB_METHOD_LSTSQ;
+    else if (!l1 && !l2 && kw->positive) { o.method = PDSB_METHOD_NNLS; if (is_f32) o.max_iter = 200; }
+    else {
+      o.method = PDSB_METHOD_CD;
+      if (!l1) { o.l1_reg = 0.0; o.positive = 1; }
+      if (is_f32) o.max_iter = 2000;
+    }
+  }
   int64_t* doff = bag.alloc<int64_t>((size_t)n_groups + 1);
   double* dbeta = bag.alloc<double>((size_t)n_groups * q);
   int* dst = bag.alloc<int>((size_t)n_groups);

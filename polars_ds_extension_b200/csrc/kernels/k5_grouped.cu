@@ -13,12 +13,14 @@
 // HBM-bound: algorithmic bytes per row = (p+1) * s.
 #include "../common.h"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace pdsb {
 
 namespace {
 
 constexpr int CHUNK = 8192;  // rows per (group, chunk) work item
+constexpr int GEN_ACC = 70;   // moments per lane of the generic-p kernel: (p+2)(p+3)/2 <= 2240 -> p <= 64
 
 // ---------------- pass 0: work list ----------------
 __global__ void count_items_kernel(const int64_t* __restrict__ offsets, int64_t n_groups, int64_t* __restrict__ item_start) {
@@ -113,6 +115,81 @@ group_moments_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__
   }
 }
 
+// 16-byte-load variant (the production pass 1 when the columns are 16-byte aligned): a lane owns V = 16 / sizeof(T)
+// CONSECUTIVE rows per load, so one warp instruction reads 512 contiguous bytes of a column and a trip of U loads per
+// column reads U x 512 B of it.  The scalar kernel above touches every column in 128-byte pieces; with p + 1 column
+// streams per warp and thousands of warps that pattern capped at ~4.3 TB/s (65 % of the HBM peak, the same ceiling the
+// Gram kernel measured on column-major frames) — longer runs per column are what DRAM pages want.
+// Rows of the 16-byte groups that fall outside [r0, r1) are masked (groups start at arbitrary rows).
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { using type = float4; static constexpr int V = 4; };
+template <> struct Vec16<double> { using type = double2; static constexpr int V = 2; };
+__device__ __forceinline__ float vget(const float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
+__device__ __forceinline__ double vget(const double2& v, int e) { return e == 0 ? v.x : v.y; }
+
+template <typename T, int P>
+__global__ void __launch_bounds__(256)
+group_moments_vec_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y,
+                         const int64_t* __restrict__ offsets, const int64_t* __restrict__ item_start,
+                         int64_t n_groups, int64_t n_items, int64_t n, double* __restrict__ part /* [NM][n_items] */) {
+  using VT = typename Vec16<T>::type;
+  constexpr int V = Vec16<T>::V;
+  constexpr int Q1 = P + 2;
+  constexpr int NM = Q1 * (Q1 + 1) / 2;
+  constexpr int U = 2;                                   // loads per column and trip
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t last_vec = ((n - 1) / V) * V;            // last 16-byte group that starts inside the columns
+  for (int64_t item = warp_global; item < n_items; item += nwarps) {
+    int64_t lo = 0, hi = n_groups;
+    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (item_start[mid] <= item) lo = mid; else hi = mid; }
+    const int64_t g = lo;
+    const int64_t r0 = offsets[g] + (item - item_start[g]) * CHUNK;
+    const int64_t r1 = min(r0 + (int64_t)CHUNK, offsets[g + 1]);
+    T acc[NM];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) acc[k] = T(0);
+    for (int64_t b = (r0 / V) * V + (int64_t)V * lane; b < r1; b += (int64_t)32 * V * U) {
+      VT z[U][P + 1];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t bb = min(b + (int64_t)32 * V * u, last_vec);      // clamped address; rows past r1 are masked below
+#pragma unroll
+        for (int c = 0; c < P; ++c) z[u][c] = *reinterpret_cast<const VT*>(X + (int64_t)c * ldx + bb);
+        z[u][P] = *reinterpret_cast<const VT*>(y + bb);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const int64_t rr = b + (int64_t)32 * V * u + e;
+          T row[Q1];
+          T probe = T(0);
+#pragma unroll
+          for (int c = 0; c <= P; ++c) { row[c] = vget(z[u][c], e); probe = fma(row[c], T(0), probe); }
+          // null rows arrive as NaN (null_policy="skip"): they drop out of their group -> the whole row becomes 0
+          const bool use = (rr >= r0) && (rr < r1) && (probe == T(0));
+#pragma unroll
+          for (int c = 0; c <= P; ++c) row[c] = use ? row[c] : T(0);
+          row[P + 1] = use ? T(1) : T(0);
+          int k = 0;
+#pragma unroll
+          for (int i = 0; i < Q1; ++i)
+#pragma unroll
+            for (int j = i; j < Q1; ++j) { acc[k] = fma(row[i], row[j], acc[k]); ++k; }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NM; ++k) {
+      double v = (double)acc[k];
+      for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) part[(size_t)k * n_items + item] = v;
+    }
+  }
+}
+
 // generic-P variant: lanes still stride rows but moments are accumulated through shared memory per warp
 template <typename T>
 __global__ void __launch_bounds__(128)
@@ -133,8 +210,8 @@ group_moments_generic_kernel(const T* __restrict__ X, int64_t ldx, const T* __re
     const int64_t g = lo;
     const int64_t r0 = offsets[g] + (item - item_start[g]) * CHUNK;
     const int64_t r1 = min(r0 + (int64_t)CHUNK, offsets[g + 1]);
-    double acc[20];   // supports nm <= 640 (p <= 33)
-    for (int k = 0; k < 20; ++k) acc[k] = 0.0;
+    double acc[GEN_ACC];   // supports nm <= 32 * GEN_ACC (p <= 64)
+    for (int k = 0; k < GEN_ACC; ++k) acc[k] = 0.0;
     for (int64_t rb = r0; rb < r1; rb += 32) {
       const int64_t r = rb + lane;
       bool fin = r < r1;
@@ -170,6 +247,7 @@ group_moments_generic_kernel(const T* __restrict__ X, int64_t ldx, const T* __re
 struct GroupSolveArgs {
   const double* part; const int64_t* item_start; const int64_t* offsets;
   int64_t n_groups, n_items; int p, add_bias, solver; double l2, tol;
+  int method, positive, max_iter; double l1, cd_tol;      // PDSB_METHOD_CD / _NNLS per group (lr_solvers.rs:426-600)
   double* ws;      // [(q*q + 2q) ][n_groups]  interleaved
   double* beta;    // [n_groups][q]
   int* status;
@@ -201,10 +279,66 @@ __global__ void __launch_bounds__(128) group_solve_kernel(GroupSolveArgs a) {
   for (int j = 0; j < q; ++j)
     for (int i = 0; i <= j; ++i) {
       double v = mom(midx(fz(i), fz(j)));
-      if (i == j && i < p && a.l2 > 0.0) v += a.l2;
+      if (a.method == PDSB_METHOD_LSTSQ && i == j && i < p && a.l2 > 0.0) v += a.l2;   // ridge; CD scales l2 by n itself
       AA(i, j) = v; AA(j, i) = v;
     }
   for (int i = 0; i < q; ++i) BB(i) = mom(midx(fz(i), p));
+  if (a.method == PDSB_METHOD_CD || a.method == PDSB_METHOD_NNLS) {
+    // Iterative solvers on the group's Gram, one thread per group (same recurrences as the single-problem kernel,
+    // k3_solve.cu; faer_coordinate_descent lr_solvers.rs:426-538, faer_nn_lr :542-600).  The ridge term a.l2 was added to
+    // the diagonal above only for LSTSQ callers: CD scales its penalties by the row count itself.
+    for (int i = 0; i < q; ++i) CN(i) = 0.0;                      // beta
+    if (a.method == PDSB_METHOD_CD) {
+      const double mcount = (double)nrows, lambda_l1 = mcount * a.l1, l2n = mcount * a.l2;
+      const double y_sum = mom(midx(p, p + 1));
+      for (int it = 0; it < a.max_iter; ++it) {
+        double max_change = 0.0;
+        for (int j = 0; j < p; ++j) {
+          const double before = CN(j);
+          double part = 0.0;
+          for (int i = 0; i < q; ++i) if (i != j) part += AA(i, j) * CN(i);
+          const double mu = BB(j) - part;
+          double after;
+          if (a.positive && mu < 0.0) after = 0.0;
+          else {
+            const double sgn = (mu > 0.0) ? 1.0 : ((mu < 0.0) ? -1.0 : 0.0);
+            after = sgn * fmax(fabs(mu) - lambda_l1, 0.0) / (AA(j, j) + l2n);
+          }
+          CN(j) = after;
+          max_change = fmax(max_change, fabs(after - before));
+        }
+        if (a.add_bias) {
+          double part = 0.0;
+          for (int j = 0; j < p; ++j) part += CN(j) * mom(midx(j, p + 1));
+          CN(p) = (y_sum - part) / mcount;
+        }
+        if (max_change < a.cd_tol) break;
+      }
+    } else {
+      // mu = G beta - X'y lives in the b slots (negated X'y to start with)
+      for (int i = 0; i < q; ++i) BB(i) = -BB(i);
+      for (int it = 0; it < a.max_iter; ++it) {
+        bool ok = true;
+        for (int i = 0; i < q; ++i) {
+          const double mu = BB(i);
+          if (!(mu >= -a.cd_tol)) ok = false;
+          if (CN(i) > 0.0 && !(mu <= a.cd_tol)) ok = false;
+        }
+        if (ok) break;
+        for (int k = 0; k < q; ++k) {
+          const double bk = CN(k);
+          double upd = bk - BB(k) / AA(k, k);
+          if (!a.add_bias || k < q - 1) upd = fmax(upd, 0.0);
+          const double diff = upd - bk;
+          for (int i = 0; i < q; ++i) BB(i) += diff * AA(i, k);
+          CN(k) = upd;
+        }
+      }
+    }
+    for (int i = 0; i < q; ++i) out[i] = CN(i);
+    a.status[g] = PDSB_OK;
+    return;
+  }
   const bool gated = a.tol > 0.0;
   double ln_den = 0.0;
   if (gated) {
@@ -217,7 +351,7 @@ __global__ void __launch_bounds__(128) group_solve_kernel(GroupSolveArgs a) {
     if (isnan(ln_den)) { a.status[g] = PDSB_OK; for (int k = 0; k < q; ++k) out[k] = nan(""); return; }
   }
   const double ln_tol = gated ? log(a.tol) : 0.0;
-  int perm[64];
+  int perm[66];
   bool done = false;
   if (a.solver == PDSB_SOLVER_CHOLESKEY) {
     bool ok = true;
@@ -241,7 +375,7 @@ __global__ void __launch_bounds__(128) group_solve_kernel(GroupSolveArgs a) {
       for (int j = 0; j < q; ++j)
         for (int i = 0; i <= j; ++i) {
           double v = mom(midx(fz(i), fz(j)));
-          if (i == j && i < p && a.l2 > 0.0) v += a.l2;
+          if (a.method == PDSB_METHOD_LSTSQ && i == j && i < p && a.l2 > 0.0) v += a.l2;   // ridge; CD scales l2 by n itself
           AA(i, j) = v; AA(j, i) = v;
         }
       for (int i = 0; i < q; ++i) BB(i) = mom(midx(fz(i), p));
@@ -305,10 +439,17 @@ __global__ void __launch_bounds__(128) group_solve_kernel(GroupSolveArgs a) {
 
 template <typename T, int P>
 int launch_moments_p(const T* X, int64_t ldx, const T* y, const int64_t* offsets, const int64_t* item_start,
-                     int64_t n_groups, int64_t n_items, double* part, cudaStream_t s) {
+                     int64_t n_groups, int64_t n_items, int64_t n, double* part, cudaStream_t s) {
   int64_t warps = n_items;
   int grid = (int)std::min<int64_t>(ceil_div(warps, 8), (int64_t)sm_count() * 16);
   if (grid < 1) grid = 1;
+  constexpr int V = 16 / (int)sizeof(T);
+  static const bool vec_on = [] { const char* e = getenv("PDSB_K5_VEC"); return !(e && e[0] == '0'); }();
+  const bool aligned = (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0) &&
+                       (ldx % V == 0) && (ldx >= ((n + V - 1) / V) * V);
+  if (vec_on && aligned && P <= 10)
+    group_moments_vec_kernel<T, P><<<grid, 256, 0, s>>>(X, ldx, y, offsets, item_start, n_groups, n_items, n, part);
+  else
   group_moments_kernel<T, P><<<grid, 256, 0, s>>>(X, ldx, y, offsets, item_start, n_groups, n_items, part);
   PDSB_LAUNCH_OK();
   count_launch();
@@ -321,9 +462,12 @@ template <typename T>
 int grouped_lin_reg(const T* X, int64_t ldx, const T* y, const int64_t* offsets, int64_t n_groups, int64_t n,
                     int p, const pdsb_solve_opts& o, double* beta, int* status, cudaStream_t s) {
   if (n_groups <= 0) return 0;
-  if (o.method != PDSB_METHOD_LSTSQ) { set_error("grouped lin_reg: only OLS / ridge is batched"); return 1; }
+  if (o.method != PDSB_METHOD_LSTSQ && o.method != PDSB_METHOD_CD && o.method != PDSB_METHOD_NNLS) {
+    set_error("grouped lin_reg: method %d is not batched", o.method);
+    return 1;
+  }
   const int q = p + (o.add_bias ? 1 : 0);
-  if (p < 1 || p > 33 || q > 64) { set_error("grouped lin_reg: p=%d not supported (1..33)", p); return 1; }
+  if (p < 1 || p > 64) { set_error("grouped lin_reg: p=%d not supported (1..64)", p); return 1; }
   const int q1 = p + 2, nm = q1 * (q1 + 1) / 2;
   // work list: we need n_items on the host to size the partial buffer -> one small D2H
   int64_t* item_start = nullptr;
@@ -338,7 +482,7 @@ int grouped_lin_reg(const T* X, int64_t ldx, const T* y, const int64_t* offsets,
   double* part = nullptr;
   if (dev_alloc((void**)&part, (size_t)nm * n_items * sizeof(double), s)) { dev_free(item_start, s); return 1; }
   int rc = 0;
-#define CASE_P(PP) case PP: rc = launch_moments_p<T, PP>(X, ldx, y, offsets, item_start, n_groups, n_items, part, s); break;
+#define CASE_P(PP) case PP: rc = launch_moments_p<T, PP>(X, ldx, y, offsets, item_start, n_groups, n_items, n, part, s); break;
   switch (p) {
     CASE_P(1) CASE_P(2) CASE_P(3) CASE_P(4) CASE_P(5) CASE_P(6) CASE_P(7) CASE_P(8) CASE_P(9) CASE_P(10)
     default: {
@@ -358,6 +502,7 @@ int grouped_lin_reg(const T* X, int64_t ldx, const T* y, const int64_t* offsets,
     GroupSolveArgs a;
     a.part = part; a.item_start = item_start; a.offsets = offsets; a.n_groups = n_groups; a.n_items = n_items;
     a.p = p; a.add_bias = o.add_bias; a.solver = o.solver; a.l2 = o.l2_reg; a.tol = o.singular_x_tol;
+    a.method = o.method; a.positive = o.positive; a.max_iter = o.max_iter; a.l1 = o.l1_reg; a.cd_tol = o.tol;
     a.ws = ws; a.beta = beta; a.status = status;
     group_solve_kernel<<<(int)ceil_div(n_groups, 128), 128, 0, s>>>(a);
     cudaError_t e = cudaGetLastError();

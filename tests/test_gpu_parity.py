@@ -246,3 +246,44 @@ def test_pageable_inputs_take_the_staged_route_and_match_pinned(monkeypatch):
     b = _harness.call_plugin("pl_lr_pred_f32", [pa.array(c) for c in pinned], names, kw)
     assert lib().pdsb_last_staged_bytes() == 0
     assert a.field("pred").equals(b.field("pred")) and a.field("resid").equals(b.field("resid"))
+
+
+@pytest.mark.parametrize("f64", [True, False])
+@pytest.mark.parametrize("kind", ["lasso", "enet", "nnls", "positive_ridge", "wide"])
+def test_grouped_iterative_and_wide(monkeypatch, f64, kind):
+    """The batched group_by entry beyond OLS / ridge: lasso, elastic net, NNLS and positive ridge per group on the reduced
+    Grams (one launch sequence instead of one ABI call per group), and p > 33 features per group.  Checked against the
+    same expression evaluated group by group through the standard symbol (the path Polars itself takes) and against the
+    oracle."""
+    monkeypatch.setattr(cfg, "LIN_REG_EXPR_F64", f64)
+    rng = np.random.default_rng(77)
+    p = 40 if kind == "wide" else 5
+    sizes = rng.integers(600, 1500, 24).tolist()
+    gid = np.repeat(np.arange(len(sizes)), sizes)
+    n = len(gid)
+    X = np.abs(rng.standard_normal((n, p))) if kind in ("nnls", "positive_ridge") else rng.standard_normal((n, p))
+    beta = np.abs(((np.arange(p) % 7) - 3) / 4.0) if kind in ("nnls", "positive_ridge") else ((np.arange(p) % 7) - 3) / 4.0
+    y = X @ beta + 0.1 * rng.standard_normal(n) + 0.5
+    dt = np.float64 if f64 else np.float32
+    df = Frame({f"x{i}": X[:, i].astype(dt) for i in range(p)} | {"y": y.astype(dt)}).with_columns(g=gid)
+    xs = [f"x{i}" for i in range(p)]
+    make = {
+        "lasso": lambda: pds.lin_reg(*xs, target="y", add_bias=True, l1_reg=0.01, tol=1e-9, max_iter=5000),
+        "enet": lambda: pds.lin_reg(*xs, target="y", add_bias=False, l1_reg=0.01, l2_reg=0.02, tol=1e-9, max_iter=5000),
+        "nnls": lambda: pds.lin_reg(*xs, target="y", add_bias=True, positive=True, tol=1e-10, max_iter=5000),
+        "positive_ridge": lambda: pds.lin_reg(*xs, target="y", add_bias=False, positive=True, l2_reg=0.05, tol=1e-9, max_iter=5000),
+        "wide": lambda: pds.lin_reg(*xs, target="y", add_bias=True, l2_reg=0.1),
+    }[kind]
+    e = make()
+    fast = GPU.group_eval(df, "g", e, fast=True)
+    slow = GPU.group_eval(df, "g", e, fast=False)
+    assert len(fast) == len(sizes)
+    for g in range(len(sizes)):
+        # same arithmetic (f64 iterations on the f64-accumulated Gram): only the moments' summation order differs
+        assert _rel(fast[g], slow[g]) < (1e-9 if f64 else 2e-5), (kind, g)
+    for g in (0, 7, 23):
+        sub = df.filter(gid == g)
+        monkeypatch.setattr(cfg, "LIN_REG_EXPR_F64", f64)
+        o = ORC.eval(sub, make())
+        tol = 1e-6 if f64 else (1e-4 if kind == "wide" else 2e-3)     # f32 twin: 200 / 2000 fixed sweeps, optimiser resolution
+        assert _rel(fast[g], o) < tol, (kind, g)
