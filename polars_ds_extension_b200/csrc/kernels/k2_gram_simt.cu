@@ -401,6 +401,131 @@ static int launch_dmma_staged(const double* X, int64_t ldx, const double* Y, int
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// m16n8k8 variant (production): the same data flow as gram_dmma_kernel with the larger FP64 tensor-core shape.
+// An 8-row step gives every lane two elements per 8-column block, Z~[k0 + l%4][8b + l/4] and Z~[k0 + l%4 + 4][8b + l/4];
+// they are the B fragment (8 x 8, "col") of block b and one half of the A fragment (16 x 8, "row") of the block pair
+// that contains b.  A block pair I (16 columns) meets block J (8 columns) in one mma.sync.m16n8k8 (2048 flops); only
+// the pairs that touch the upper triangle (J >= 2 I) are issued: 9 instructions per 8 rows at 33..40 columns, where the
+// m8n8k4 kernel issues 30.  Round 2 measured the m8n8k4 kernel at 33 % of the HBM peak with the FP64 pipe far from its
+// peak: the small shape is issue-limited.
+__device__ __forceinline__ void dmma1688(double* c, double a0, double a1, double a2, double a3, double b0, double b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3]) : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(b0), "d"(b1));
+}
+
+template <int NB> struct Dmma16 {
+  static constexpr int NI = (NB + 1) / 2;                 // 16-column block pairs
+  static constexpr int count() { int c = 0; for (int i = 0; i < NI; ++i) for (int j = 2 * i; j < NB; ++j) ++c; return c; }
+  static constexpr int NMMA = count();
+};
+
+constexpr int D16_WARPS = 4;   // 128-thread CTAs: 152 registers at 33..40 columns -> 3 CTAs (12 warps) per SM
+template <int NB>
+__global__ void __launch_bounds__(D16_WARPS * 32)
+gram_dmma16_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
+                   const double* __restrict__ w, const double* __restrict__ mask, int64_t n, int p, int t,
+                   double* __restrict__ partials /* [grid][q1*q1] */) {
+  constexpr int NI = Dmma16<NB>::NI, NMMA = Dmma16<NB>::NMMA;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);      // [NMMA][128] CTA-level sum of the warps' accumulators
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, k = lane & 3;
+  const int q1 = p + t + 1;
+  const double* colp[NB];
+  int kind[NB];                                           // 0 data, 1 ones / mask, 2 zero padding
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int c = 8 * b + g;
+    kind[b] = c < p + t ? 0 : (c == p + t ? 1 : 2);
+    colp[b] = c < p ? X + (int64_t)c * ldx : (c < p + t ? Y + (int64_t)(c - p) * ldy : X);
+  }
+  double acc[NMMA][4];
+#pragma unroll
+  for (int i = 0; i < NMMA; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; acc[i][2] = 0.0; acc[i][3] = 0.0; }
+
+  const int64_t stride = (int64_t)gridDim.x * D16_WARPS * 8;
+  auto load_step = [&](int64_t r0, double (*z)[2], double* wv) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t r = r0 + k + 4 * h;
+      const bool in = r < n;
+      wv[h] = (in && w) ? w[r] : 1.0;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        double v = 0.0;
+        if (in) {
+          if (kind[b] == 0) v = colp[b][r];
+          else if (kind[b] == 1) v = mask ? mask[r] : 1.0;
+        }
+        z[b][h] = v;
+      }
+    }
+  };
+  int64_t r0 = ((int64_t)blockIdx.x * D16_WARPS + warp) * 8;
+  double z[NB][2], zn[NB][2], wv[2] = {1.0, 1.0}, wn[2] = {1.0, 1.0};
+  if (r0 < n) load_step(r0, z, wv);
+  for (; r0 < n; r0 += stride) {
+    const bool more = r0 + stride < n;
+    if (more) load_step(r0 + stride, zn, wn);             // next step's loads fly while this step's DMMAs issue
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      // A fragment of the block pair (2i, 2i+1): a0 (row g, k), a1 (row g+8, k), a2 (row g, k+4), a3 (row g+8, k+4)
+      const double a0 = z[2 * i][0] * wv[0], a2 = z[2 * i][1] * wv[1];
+      const double a1 = (2 * i + 1 < NB) ? z[2 * i + 1 < NB ? 2 * i + 1 : 0][0] * wv[0] : 0.0;
+      const double a3 = (2 * i + 1 < NB) ? z[2 * i + 1 < NB ? 2 * i + 1 : 0][1] * wv[1] : 0.0;
+#pragma unroll
+      for (int j = 2 * i; j < NB; ++j) { dmma1688(acc[idx], a0, a1, a2, a3, z[j][0], z[j][1]); ++idx; }
+    }
+    if (more) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) { z[b][0] = zn[b][0]; z[b][1] = zn[b][1]; }
+      wv[0] = wn[0]; wv[1] = wn[1];
+    }
+  }
+  // ---- CTA reduction in a fixed order: warp 0 stores, the other warps add one after the other ----
+  // C fragment of (I, J): c0 (row g, col 2k), c1 (g, 2k+1), c2 (g+8, 2k), c3 (g+8, 2k+1); tile slot = row * 8 + col
+  for (int wturn = 0; wturn < D16_WARPS; ++wturn) {
+    if (warp == wturn) {
+#pragma unroll
+      for (int i = 0; i < NMMA; ++i) {
+        double* d = sm + i * 128;
+        const int s0 = g * 8 + 2 * k, s1 = (g + 8) * 8 + 2 * k;
+        if (wturn == 0) { d[s0] = acc[i][0]; d[s0 + 1] = acc[i][1]; d[s1] = acc[i][2]; d[s1 + 1] = acc[i][3]; }
+        else { d[s0] += acc[i][0]; d[s0 + 1] += acc[i][1]; d[s1] += acc[i][2]; d[s1 + 1] += acc[i][3]; }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- this CTA's partial, full symmetric q1 x q1 ----
+  double* out = partials + (size_t)blockIdx.x * q1 * q1;
+  for (int e = threadIdx.x; e < NMMA * 128; e += D16_WARPS * 32) {
+    const int blk = e >> 7, rr = (e >> 3) & 15, cc = e & 7;
+    int i = 0, rem = blk;
+    while (rem >= NB - 2 * i) { rem -= NB - 2 * i; ++i; }
+    const int j = 2 * i + rem;
+    const int a = 16 * i + rr, b = 8 * j + cc;
+    if (a < q1 && b < q1 && a <= b) {
+      const double v = sm[e];
+      out[(size_t)a * q1 + b] = v;
+      out[(size_t)b * q1 + a] = v;
+    }
+  }
+}
+
+template <int NB>
+static int launch_dmma16(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w, const double* mask,
+                         int64_t n, int p, int t, int grid, double* partials, cudaStream_t s) {
+  const size_t smem = (size_t)Dmma16<NB>::NMMA * 128 * sizeof(double);
+  auto k = gram_dmma16_kernel<NB>;
+  if (smem > 48 * 1024) PDSB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, D16_WARPS * 32, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, partials);
+  PDSB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
 template <int NB>
 static int launch_dmma(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w, const double* mask,
                        int64_t n, int p, int t, int grid, double* partials, cudaStream_t s) {
@@ -419,7 +544,10 @@ static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64
   const int nb = (q1 + 7) / 8;
   if (!enabled || nb < 1 || nb > 8 || n < 1) return -1;
   // staged kernel for the whole 128-row tiles (needs 16-byte aligned columns), direct kernel for the rest
-  static const bool staged_on = [] { const char* e = getenv("PDSB_K2A_STAGED"); return !(e && e[0] == '0'); }();
+  // PDSB_K2A_KERNEL: 16 (default) = m16n8k8 direct, 8 = m8n8k4 direct, 0 = bulk-copy staged m8n8k4 (+ m8n8k4 tail).
+  // Measured (B200, 2e7 x 33 f64): staged 22.9 %, m8n8k4 direct 33.4 % of the HBM peak — see profiles/README.md.
+  static const int kern = [] { const char* e = getenv("PDSB_K2A_KERNEL"); return e ? atoi(e) : 16; }();
+  const bool staged_on = kern == 0;
   const int ncol = p + t + (w ? 1 : 0) + (mask ? 1 : 0);
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const bool aligned = al16(X) && al16(Y) && (ldx % 2 == 0) && (ldy % 2 == 0) && (!w || al16(w)) && (!mask || al16(mask));
@@ -436,7 +564,10 @@ static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64
     const int per_sm = smem_need <= 100 * 1024 ? 2 : 1;
     grid_main = (int)std::min<int64_t>(ntiles, (int64_t)sm_count() * per_sm);
   }
-  if (n_tail > 0) grid = (int)std::min<int64_t>(ceil_div(n_tail, 32), (int64_t)sm_count() * 4);
+  if (n_tail > 0) {
+    if (kern == 16) grid = (int)std::min<int64_t>(ceil_div(n_tail, 8 * D16_WARPS), (int64_t)sm_count() * (nb <= 4 ? 4 : (nb <= 5 ? 3 : 2)));
+    else grid = (int)std::min<int64_t>(ceil_div(n_tail, 32), (int64_t)sm_count() * 4);
+  }
   if (grid_main + grid < 1) grid = 1;
   double* partials = nullptr;
   if (dev_alloc((void**)&partials, (size_t)(grid_main + grid) * q1 * q1 * sizeof(double), s)) return 1;
@@ -455,6 +586,18 @@ static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64
     const double* Xt = X + n_main; const double* Yt = Y + n_main;
     const double* wt = w ? w + n_main : nullptr; const double* mt = mask ? mask + n_main : nullptr;
     double* pt = partials + (size_t)grid_main * q1 * q1;
+    if (kern == 16) {
+      switch (nb) {
+        case 1: rc = launch_dmma16<1>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+        case 2: rc = launch_dmma16<2>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+        case 3: rc = launch_dmma16<3>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+        case 4: rc = launch_dmma16<4>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+        case 5: rc = launch_dmma16<5>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+        case 6: rc = launch_dmma16<6>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+        case 7: rc = launch_dmma16<7>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+        default: rc = launch_dmma16<8>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+      }
+    } else
     switch (nb) {
       case 1: rc = launch_dmma<1>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
       case 2: rc = launch_dmma<2>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;

@@ -486,34 +486,36 @@ __device__ __forceinline__ void put_products(float* __restrict__ tile, int lane,
   out[(size_t)(NM - 1) * ST] = BOTH ? __fadd2_rn(ef, __fmul2_rn(lf, bc(-1.0f))) : ef;
 }
 
-// moment lanes: in-place inclusive scan of the 64 rows of their moments; returns the step totals
+// moment lanes: in-place inclusive scan of the 64 rows of their moments; returns the step totals.
+// Two levels, so that nothing but a 16-long carry chain is serial: all 16 LDS.128 of a row are issued at once, the four
+// values of every float4 are prefix-summed independently (16-way ILP), the carries run over the 16 group totals, and the
+// carry is added back with packed adds.  (The first version walked the 64 values in one dependent LDS -> FADD chain:
+// ncu attributed a quarter of all stall samples to those FADDs waiting on shared-memory loads.)
 template <int D>
 __device__ __forceinline__ void scan_products(float* __restrict__ tile, int lane, float* tot) {
   constexpr int NM = V2<D>::NM, TPL = V2<D>::TPL;
-  float s[TPL];
-  float4* row[TPL];
 #pragma unroll
   for (int m = 0; m < TPL; ++m) {
-    s[m] = 0.0f;
-    const int k = min(lane + 32 * m, NM - 1);                // idle lanes rescan the last moment's row: harmless? no -> guarded below
-    row[m] = reinterpret_cast<float4*>(tile + (size_t)k * SBP);
-  }
-#pragma unroll 4
-  for (int i = 0; i < SB / 4; ++i) {
+    tot[m] = 0.0f;
+    if (lane + 32 * m < NM) {
+      float4* row = reinterpret_cast<float4*>(tile + (size_t)(lane + 32 * m) * SBP);
+      float4 v[SB / 4];
 #pragma unroll
-    for (int m = 0; m < TPL; ++m) {
-      if (lane + 32 * m < NM) {
-        float4 v = row[m][i];
-        s[m] += v.x; v.x = s[m];
-        s[m] += v.y; v.y = s[m];
-        s[m] += v.z; v.z = s[m];
-        s[m] += v.w; v.w = s[m];
-        row[m][i] = v;
+      for (int i = 0; i < SB / 4; ++i) v[i] = row[i];
+#pragma unroll
+      for (int i = 0; i < SB / 4; ++i) { v[i].y += v[i].x; v[i].w += v[i].z; v[i].z += v[i].y; v[i].w += v[i].y; }
+      float c = 0.0f;
+#pragma unroll
+      for (int i = 0; i < SB / 4; ++i) {
+        const float t = v[i].w;
+        const float2 lo = __fadd2_rn(make_float2(v[i].x, v[i].y), make_float2(c, c));
+        const float2 hi = __fadd2_rn(make_float2(v[i].z, v[i].w), make_float2(c, c));
+        row[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        c += t;
       }
+      tot[m] = c;
     }
   }
-#pragma unroll
-  for (int m = 0; m < TPL; ++m) tot[m] = s[m];
 }
 
 // packed Cholesky solve of two rows at once (same algorithm as chol_solve_packed)
