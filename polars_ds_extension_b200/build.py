@@ -56,7 +56,7 @@ def _compile(src: str, force: bool, hm: float, verbose: bool) -> Path:
     o = OBJ / (src.replace("/", "_") + ".o")
     if not force and o.exists() and o.stat().st_mtime > max(s.stat().st_mtime, hm):
         return o
-    cmd = [NVCC, *ARCH, *COMMON, "-c", str(s), "-o", str(o)]
+    cmd = [NVCC, *ARCH, *COMMON, *os.environ.get("PDSB_EXTRA_NVCC_FLAGS", "").split(), "-c", str(s), "-o", str(o)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
