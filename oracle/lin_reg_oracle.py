@@ -758,3 +758,107 @@ def window_ols(X, y, lo, hi, lam=0.0, add_bias=False):
     n1 = Xw.shape[1]
     G[np.arange(n1), np.arange(n1)] += lam
     return np.linalg.solve(G, Xw.T @ np.asarray(y[lo:hi], dtype=np.float64))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# logistic regression: src/num_ext/logistic_regression.rs:10-99, solver src/linear/logistic/logistic_solver.rs
+# ---------------------------------------------------------------------------------------------------------------------
+def stable_sigmoid(x):
+    """logistic_solver.rs:10-18"""
+    x = np.asarray(x, dtype=np.float64)
+    r = 1.0 / (1.0 + np.exp(-np.abs(x)))
+    return np.where(x >= 0.0, r, 1.0 - r)
+
+
+def stable_log_loss(y, z):
+    """logistic_solver.rs:22-25"""
+    return np.maximum(z, 0.0) - y * z + np.log1p(np.exp(-np.abs(z)))
+
+
+def faer_logistic_reg(X, y, add_bias: bool, l1_reg, l2_reg, tol: float, max_iters: int):
+    """logistic_solver.rs:107-146: argmin's L-BFGS (history 10, More-Thuente line search; OWL-QN when l1 > 0) on
+    cost(w) = mean stable_log_loss(y, X w) + l2 / 2 |w_features|^2 (:42-74), gradient X'(sigmoid(Xw) - y) / m + l2 w
+    (:80-103), from N(0, 0.01) draws of StdRng(42) (:121-124), gradient tolerance max(sqrt(eps), tol) (:127).
+    argmin (Cargo.lock: argmin 0.10) is not vendored; the cost is convex, so its minimiser is restated through SciPy's
+    L-BFGS-B on the same cost / gradient from a zero start, to a gradient tolerance below the reference's.  With l1 the
+    non-smooth term is handled by a proximal-Newton loop (coordinate descent on the quadratic model), the optimum OWL-QN
+    converges to.  X already holds the ones column when add_bias (logistic_regression.rs:27-31)."""
+    from scipy.optimize import minimize
+
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    m, q = X.shape
+    nfeat = q - int(add_bias)
+    l2 = l2_reg if (l2_reg is not None and l2_reg > 0.0) else 0.0
+    l1 = max(l1_reg, np.finfo(np.float64).eps) if (l1_reg is not None and l1_reg > 0.0) else 0.0
+    gtol = max(np.sqrt(np.finfo(np.float64).eps), tol)
+
+    def cost(w):
+        z = X @ w
+        return stable_log_loss(y, z).sum() / m + 0.5 * l2 * float(w[:nfeat] @ w[:nfeat])
+
+    def grad(w):
+        g = X.T @ (stable_sigmoid(X @ w) - y) / m
+        g[:nfeat] += l2 * w[:nfeat]
+        return g
+
+    if l1 == 0.0:
+        res = minimize(cost, np.zeros(q), jac=grad, method="L-BFGS-B",
+                       options={"maxiter": max(int(max_iters), 1) * 10, "gtol": min(gtol, 1e-9) * 1e-2, "ftol": 1e-16, "maxcor": 10})
+        w = res.x
+        for _ in range(50):                 # polish with Newton steps: the oracle is the exact minimiser
+            mu = stable_sigmoid(X @ w)
+            H = (X * (mu * (1.0 - mu))[:, None]).T @ X / m
+            H[:nfeat, :nfeat] += l2 * np.eye(nfeat)
+            g = grad(w)
+            if np.linalg.norm(g) < 1e-13:
+                break
+            w = w - np.linalg.solve(H, g)
+        return w
+    # proximal Newton with coordinate descent on the l1-penalised quadratic model
+    w = np.zeros(q)
+    for _ in range(200):
+        z = X @ w
+        mu = stable_sigmoid(z)
+        wt = np.maximum(mu * (1.0 - mu), 1e-12)
+        zz = z + (y - mu) / wt
+        A = (X * wt[:, None]).T @ X / m
+        b = X.T @ (wt * zz) / m
+        w_new = w.copy()
+        for _cd in range(5000):
+            dmax = 0.0
+            for j in range(q):
+                r = b[j] - A[j] @ w_new + A[j, j] * w_new[j]
+                if j < nfeat:
+                    v = np.sign(r) * max(abs(r) - l1, 0.0) / (A[j, j] + l2)
+                else:
+                    v = r / A[j, j]
+                dmax = max(dmax, abs(v - w_new[j]))
+                w_new[j] = v
+            if dmax < 1e-14:
+                break
+        done = np.max(np.abs(w_new - w)) < 1e-12
+        w = w_new
+        if done:
+            break
+    return w
+
+
+def pl_logistic_coeffs(inputs: Sequence[Col], kw: dict, f32: bool = False):
+    """logistic_regression.rs:10-48 -> coeffs [q] (float64, bias last)."""
+    policy = parse_null_policy(kw["null_policy"])
+    y, X, _ = series_to_mat_for_lr(inputs, kw["bias"], policy, np.float64)
+    return faer_logistic_reg(X, y, kw["bias"], kw.get("l1_reg", 0.0), kw.get("l2_reg", 0.0), kw.get("tol", 1e-5), kw.get("max_iter", 200))
+
+
+def pl_logistic_pred(inputs: Sequence[Col], kw: dict, f32: bool = False):
+    """logistic_regression.rs:50-99 -> (probabilities, valid): nulls re-inserted where the null policy dropped the row."""
+    policy = parse_null_policy(kw["null_policy"])
+    y, X, mask = series_to_mat_for_lr(inputs, kw["bias"], policy, np.float64)
+    w = faer_logistic_reg(X, y, kw["bias"], kw.get("l1_reg", 0.0), kw.get("l2_reg", 0.0), kw.get("tol", 1e-5), kw.get("max_iter", 200))
+    pred = stable_sigmoid(X @ w)
+    if isinstance(mask, np.ndarray) and (~mask).any():
+        out = np.zeros(len(mask))
+        out[mask] = pred
+        return out, mask.copy()
+    return pred, np.ones(len(pred), dtype=bool)

@@ -2,7 +2,7 @@
 
 The product is the shared library `_polars_ds_b200.so` (hand-written sm_100a CUDA behind the Polars plugin C ABI and
 the `pdsb_*` C API, see include/).  This package holds the host-side mirror of the reference's Python wrappers
-(`pds.lin_reg`, `simple_lin_reg`, `lin_reg_report`, `rolling_lin_reg`, `recursive_lin_reg`, `lin_reg_w_rcond`), the
+(`pds.lin_reg`, `logistic_reg`, `simple_lin_reg`, `lin_reg_report`, `rolling_lin_reg`, `recursive_lin_reg`, `lin_reg_w_rcond`), the
 numpy-facing model classes (`linear_models.LR / ElasticNet / OnlineLR`) and a Polars-free harness that calls the plugin
 symbols exactly the way Polars does.
 """
@@ -12,6 +12,7 @@ from .exprs.expr_linear import (  # noqa: F401
     lin_reg_report,
     lin_reg_w_rcond,
     linear_impute,
+    logistic_reg,
     query_ar_coeffs,
     recursive_lin_reg,
     rolling_lin_reg,

@@ -160,4 +160,4 @@ PLUGIN_SYMBOLS = [
     for sfx in ("", "_f32")
     for base in ("pl_lr", "pl_lr_pred", "pl_lr_multi", "pl_lr_multi_pred", "pl_lr_w_rcond", "pl_lin_reg_report",
                  "pl_wls_report", "pl_recursive_lr", "pl_rolling_lr")
-]
+] + ["pl_logistic_coeffs", "pl_logistic_pred"]        # float64 only, like the reference (logistic_regression.rs:10-99)

@@ -29,6 +29,7 @@ SOURCES = [
     "kernels/k6_online.cu",
     "kernels/k9_report.cu",
     "kernels/k10_models.cu",
+    "kernels/k11_logistic.cu",
     "host/context.cc",
     "host/api_dev.cc",
     "host/h2d.cc",

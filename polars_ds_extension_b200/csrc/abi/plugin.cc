@@ -477,6 +477,26 @@ void run_online(SeriesExport* in, size_t n, const uint8_t* kwp, size_t kwn, Seri
   sr_unref(sr);
 }
 
+// pl_logistic_coeffs / pl_logistic_pred (logistic_regression.rs:10-99): LRKwargs, Float64 outputs
+void run_logistic(SeriesExport* in, size_t n, const uint8_t* kwp, size_t kwn, SeriesExport* ret, bool pred) {
+  fail(ret);
+  Imported im;
+  if (!import_inputs(in, n, im)) return;
+  Kwargs kw;
+  if (!load_kwargs(kwp, kwn, kw, REQ_LR)) return;
+  SharedResult* sr = new SharedResult();
+  if (pdsb_host_logistic(im.cols.data(), (int)n, &kw.k, pred, &sr->r)) { sr_unref(sr); return; }
+  const pdsb_host_result& r = sr->r;
+  if (!pred) {
+    auto root = list_node("coeffs", false, r.coeffs, 1, r.n_coef, nullptr, false);
+    export_series(*root, sr, ret);
+  } else {
+    auto root = prim_node("pred", false, r.pred, r.n_rows, r.valid, false);
+    export_series(*root, sr, ret);
+  }
+  sr_unref(sr);
+}
+
 void run_by(SeriesExport* in, size_t n, const uint8_t* kwp, size_t kwn, SeriesExport* ret, bool f32) {
   fail(ret);
   Imported im;
@@ -534,6 +554,8 @@ DEF_EXPR(pl_wls_report,       run_report(inputs, n_inputs, kwargs, kwargs_len, r
 DEF_EXPR(pl_recursive_lr,     run_online(inputs, n_inputs, kwargs, kwargs_len, ret, false, false),    FIELD_CP(false))
 DEF_EXPR(pl_rolling_lr,       run_online(inputs, n_inputs, kwargs, kwargs_len, ret, false, true),     FIELD_CP(false))
 DEF_EXPR(pl_lr_by,            run_by(inputs, n_inputs, kwargs, kwargs_len, ret, false),               FIELD_COEFF(false))
+DEF_EXPR(pl_logistic_coeffs,  run_logistic(inputs, n_inputs, kwargs, kwargs_len, ret, false),         FIELD_COEFF(false))
+DEF_EXPR(pl_logistic_pred,    run_logistic(inputs, n_inputs, kwargs, kwargs_len, ret, true),          { auto nd = schema_prim("pred", false); field_out(out, *nd); })
 
 DEF_EXPR(pl_lr_f32,             run_lr(inputs, n_inputs, kwargs, kwargs_len, ret, true, false, false), FIELD_COEFF(true))
 DEF_EXPR(pl_lr_pred_f32,        run_lr(inputs, n_inputs, kwargs, kwargs_len, ret, true, true, false),  FIELD_PRED(true))

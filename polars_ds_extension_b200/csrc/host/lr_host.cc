@@ -652,6 +652,130 @@ int host_grouped_t(const pdsb_column* cols, int n_cols, const int64_t* offsets, 
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// pl_logistic_coeffs / pl_logistic_pred (/root/reference/src/num_ext/logistic_regression.rs:10-99): f64 only.
+// The reference minimises mean log-loss (+ l2/2 |w|^2, + l1 |w|_1 via OWL-QN) with L-BFGS from a seeded random start
+// (logistic_solver.rs:107-146); the cost is convex, so Newton / IRLS on the device reaches the same minimiser:
+// per iteration one row pass (K11: weights + working response + loss), the weighted moments (K2a) and the ridge solve
+// (K3; coordinate descent on the weighted Gram when l1 > 0 = proximal Newton).  Stops like the reference when the
+// gradient norm falls below max(sqrt(eps), tol); step halving whenever the cost does not decrease.
+int host_logistic(const pdsb_column* cols, int n_cols, const pdsb_lr_kwargs* kw, int want_pred, pdsb_host_result* out) {
+  NvtxRange nv("pdsb:host_logistic");
+  typedef double T;
+  cudaStream_t s, s2;
+  if (thread_streams(&s, &s2)) return 1;
+  NullPolicy pol;
+  if (parse_null_policy(kw->null_policy, &pol)) return 1;
+  DevBag bag(s);
+  Frame<T> F;
+  if (build_frame<T>(cols, n_cols, 1, nullptr, pol, false, false, F, bag, s)) return 1;
+  const int p = F.p, add_bias = kw->bias ? 1 : 0, q = p + add_bias, q1 = p + 2;
+  const int64_t n = F.n;
+  if (p > 64) { set_error("logistic_reg: more than 64 features are not supported"); return 1; }
+  double m = (double)n;                       // rows that take part
+  double* dM = bag.alloc<double>((size_t)q1 * q1);
+  double* dbeta = bag.alloc<double>((size_t)q);
+  int* dstatus = bag.alloc<int>(4);
+  T* dw = bag.alloc<T>((size_t)F.ld);
+  T* dz = bag.alloc<T>((size_t)F.ld);
+  double* dparts = bag.alloc<double>((size_t)irls_max_parts() + 1);
+  if (!dM || !dbeta || !dstatus || !dw || !dz || !dparts) return 1;
+  if (F.mask) {
+    if (count_mask<T>(F.mask, n, dparts, s)) return 1;
+    PDSB_CUDA_OK(cudaMemcpyAsync(&m, dparts, sizeof(double), cudaMemcpyDeviceToHost, s));
+    PDSB_CUDA_OK(cudaStreamSynchronize(s));
+  }
+  if (m < 1.0) { set_error("Empty data"); return 1; }
+  const double l1 = kw->l1_reg > 0.0 ? std::max(kw->l1_reg, DBL_EPSILON) : 0.0;      // logistic_solver.rs:131-133
+  const double l2 = kw->l2_reg > 0.0 ? kw->l2_reg : 0.0;
+  const double gtol = std::max(std::sqrt(DBL_EPSILON), kw->tol);                      // :127
+  const int64_t max_iter = kw->max_iter > 0 ? kw->max_iter : 200;
+  std::vector<double> hb(q, 0.0), hb_prev(q, 0.0), hM((size_t)q1 * q1), hparts((size_t)irls_max_parts());
+  PDSB_CUDA_OK(cudaMemsetAsync(dbeta, 0, sizeof(double) * q, s));
+  pdsb_solve_opts o{};
+  o.p = p; o.t = 1; o.add_bias = add_bias; o.solver = PDSB_SOLVER_QR; o.singular_x_tol = 0.0; o.max_iter = 2000; o.tol = 1e-12;
+  double cost_prev = INFINITY;
+  int halvings = 0;
+  bool failed = false;
+  for (int64_t it = 0; it < max_iter; ++it) {
+    int nparts = 0;
+    if (irls_rows<T>(F.X(), F.ld, F.Y(), F.mask, n, p, add_bias, dbeta, dw, dz, dparts, &nparts, s)) return 1;
+    if (moments_simt<T>(F.X(), F.ld, dz, F.ld, dw, F.mask, n, p, 1, dM, s)) return 1;
+    PDSB_CUDA_OK(cudaMemcpyAsync(hM.data(), dM, hM.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PDSB_CUDA_OK(cudaMemcpyAsync(hparts.data(), dparts, (size_t)nparts * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PDSB_CUDA_OK(cudaStreamSynchronize(s));
+    double loss = 0.0;
+    for (int i = 0; i < nparts; ++i) loss += hparts[i];
+    double pen = 0.0, l1n = 0.0;
+    for (int j = 0; j < p; ++j) { pen += hb[j] * hb[j]; l1n += std::fabs(hb[j]); }
+    const double cost = loss / m + 0.5 * l2 * pen + l1 * l1n;
+    if (!std::isfinite(cost)) { failed = true; break; }
+    if (it > 0 && cost > cost_prev + 1e-14 * std::fabs(cost_prev) && halvings < 40) {
+      // the full Newton step overshot: halve it and evaluate again (the reference's line search plays this role)
+      for (int j = 0; j < q; ++j) hb[j] = 0.5 * (hb[j] + hb_prev[j]);
+      PDSB_CUDA_OK(cudaMemcpyAsync(dbeta, hb.data(), sizeof(double) * q, cudaMemcpyHostToDevice, s));
+      PDSB_CUDA_OK(cudaStreamSynchronize(s));
+      ++halvings;
+      continue;
+    }
+    halvings = 0;
+    // gradient of the smooth part from the weighted moments [X | z | 1]: X'(mu - y) = (X'WX) w - X'Wz
+    auto col = [&](int j) { return j < p ? j : p + 1; };          // coefficient j -> moments index (bias = the ones column)
+    double g2 = 0.0;
+    const double sum_w = hM[(size_t)(p + 1) * q1 + (p + 1)];
+    for (int j = 0; j < q; ++j) {
+      double gj = -hM[(size_t)col(j) * q1 + p];
+      for (int k = 0; k < q; ++k) gj += hM[(size_t)col(j) * q1 + col(k)] * hb[k];
+      gj = gj / m + (j < p ? l2 * hb[j] : 0.0);
+      if (l1 > 0.0 && j < p) {       // minimum-norm subgradient of the l1 term
+        if (hb[j] > 0.0) gj += l1; else if (hb[j] < 0.0) gj -= l1;
+        else gj = std::fabs(gj) <= l1 ? 0.0 : (gj > 0.0 ? gj - l1 : gj + l1);
+      }
+      g2 += gj * gj;
+    }
+    cost_prev = cost; hb_prev = hb;
+    if (std::sqrt(g2) < gtol) break;
+    if (!(sum_w > 0.0)) { failed = true; break; }
+    if (l1 > 0.0) { o.method = PDSB_METHOD_CD; o.l1_reg = l1 * m / sum_w; o.l2_reg = l2 * m / sum_w; }   // K3 scales by the count entry = sum w
+    else { o.method = PDSB_METHOD_LSTSQ; o.l1_reg = 0.0; o.l2_reg = l2 * m; }
+    if (solve_from_moments(dM, o, dbeta, dstatus, nullptr, s)) return 1;
+    PDSB_CUDA_OK(cudaMemcpyAsync(hb.data(), dbeta, sizeof(double) * q, cudaMemcpyDeviceToHost, s));
+    PDSB_CUDA_OK(cudaStreamSynchronize(s));
+    bool fin = true;
+    for (int j = 0; j < q; ++j) fin &= std::isfinite(hb[j]);
+    if (!fin) { failed = true; break; }
+  }
+  if (failed) for (int j = 0; j < q; ++j) hb_prev[j] = NAN;        // Mat::full(nrows, 1, NaN), logistic_solver.rs:141-144
+  const std::vector<double>& best = hb_prev;                      // the last accepted iterate (argmin's best_param)
+  memset(out, 0, sizeof(*out));
+  out->is_f32 = 0; out->n_coef = q; out->n_targets = 1;
+  if (!want_pred) {
+    double* c = reinterpret_cast<double*>(result_buf(out, (size_t)q * sizeof(double)));
+    if (!c) return 1;
+    for (int j = 0; j < q; ++j) c[j] = best[j];
+    out->coeffs = c;
+    return 0;
+  }
+  PDSB_CUDA_OK(cudaMemcpyAsync(dbeta, best.data(), sizeof(double) * q, cudaMemcpyHostToDevice, s));
+  if (sigmoid_predict<T>(F.X(), F.ld, n, p, add_bias, dbeta, dz, s)) return 1;
+  double* hp = reinterpret_cast<double*>(result_buf(out, (size_t)n * sizeof(double)));
+  if (!hp) return 1;
+  PDSB_CUDA_OK(cudaMemcpyAsync(hp, dz, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  uint8_t* hv = nullptr;
+  std::vector<double> hmask;
+  if (F.mask) {
+    hv = reinterpret_cast<uint8_t*>(result_buf(out, (size_t)n));
+    if (!hv) return 1;
+    hmask.resize((size_t)n);
+    PDSB_CUDA_OK(cudaMemcpyAsync(hmask.data(), F.mask, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  PDSB_CUDA_OK(cudaStreamSynchronize(s));
+  if (hv) for (int64_t i = 0; i < n; ++i) hv[i] = hmask[(size_t)i] != 0.0 ? 1 : 0;
+  out->n_rows = n; out->pred = hp; out->valid = hv;
+  return 0;
+}
+
 }  // namespace
 }  // namespace pdsb
 
@@ -691,6 +815,9 @@ int pdsb_host_online(const pdsb_column* cols, int n_cols, const pdsb_lr_kwargs* 
                      pdsb_host_result* out) {
   PDSB_GUARD(f32 ? host_online_t<float>(cols, n_cols, kw, rolling, out)
                  : host_online_t<double>(cols, n_cols, kw, rolling, out));
+}
+int pdsb_host_logistic(const pdsb_column* cols, int n_cols, const pdsb_lr_kwargs* kw, int want_pred, pdsb_host_result* out) {
+  PDSB_GUARD(host_logistic(cols, n_cols, kw, want_pred, out));
 }
 int pdsb_host_grouped_lin_reg(const pdsb_column* cols, int n_cols, const int64_t* group_offsets, int64_t n_groups,
                               const pdsb_lr_kwargs* kw, int f32, pdsb_host_result* out) {

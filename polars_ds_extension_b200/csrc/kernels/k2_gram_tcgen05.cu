@@ -3,35 +3,39 @@
 // Replaces faer's matmul in get_xtx_with_lambda / build_xty (/root/reference/src/linear/lr/lr_solvers.rs:183-211,
 // 262-278) and the column sums of faer_coordinate_descent (:483-484): one pass over the frame instead of three.
 //
-// Shape of the problem: Z~ = [Z | 1] has q~ = p + t + 1 columns and n ~ 1e8 rows, i.e. a GEMM with M = N = q~ and
-// K = n.  At q~ = 34 the FP32 SIMT pipes cannot keep up with HBM (595 FMA per row vs 132 bytes per row), so the Gram
-// goes to tcgen05.mma kind::tf32 — and because one TF32 product loses 13 mantissa bits it is computed as the classic
+// Shape of the problem: X has p <= 64 columns and n ~ 1e8 rows, i.e. a GEMM with M = N = p and K = n — tiny output,
+// enormous reduction.  At p = 32 the FP32 SIMT pipes cannot keep up with HBM (595 FMA per 132-byte row), so X'X goes
+// to tcgen05.mma kind::tf32 — and because one TF32 product loses 13 mantissa bits it is computed as the classic
 // 3-term split  x = hi + lo  (hi = x with the low 13 mantissa bits cleared, lo = x - hi, exact in fp32):
-//        G = HH + LH + LH^T (+ LL ~ 2^-22, dropped),     HH = hi^T hi,  LH = lo^T hi.
-// Both products come out of ONE instruction stream by stacking hi and lo along the MMA's M = 128 dimension (free:
-// an M = 64 and an M = 128 instruction cost the same N/2 cycles, and the tensor pipe is ~50 % busy at the HBM rate):
-//        A  (TMEM, 128 lanes x 8 columns per MMA): hi and lo of the A-side columns (layout below)
-//        B  (SMEM, N x 8, K-major, 128B swizzle)  : the TMA tile as it landed
+//        X'X = HH + LH + LH^T (+ LL ~ 2^-22, dropped),     HH = hi^T hi,  LH = lo^T hi.
+// Both products come out of ONE instruction stream by stacking hi and lo along the MMA's M = 128 dimension:
+//        A  (TMEM, 128 lanes x 8 columns per MMA): hi and lo of the feature columns (layout below)
+//        B  (SMEM, N x 8, K-major, 128B swizzle)  : the feature rows of the TMA tile as they landed, N = p padded to 16
 // The hi operand is the RAW data: the tensor core reads an fp32 operand as TF32 by ignoring the low 13 mantissa bits
 // (measured on B200: tests/test_gpu_moments.py compares against exact-product f64-accumulated moments; assuming
 // round-to-nearest instead gives 7e-4 relative error), so B needs no conversion at all and the hi lanes of A are a copy.
 //
-// A-lane layout ("16 + 16"): a warp can only write the 32 TMEM lanes of its own quadrant (warp id mod 4).  Quadrant k
-// holds columns 16k .. 16k+15 of the A side TWICE: lanes 0..15 = hi (raw), lanes 16..31 = lo.  Lane L and lane L + 16
-// read the SAME shared-memory address (a broadcast), so one LDS.128 of a converter warp touches 16 rows x 16 bytes =
-// 2 wavefronts, and every element of the tile is read from shared memory ONCE.  (Round 1 kept hi and lo in different
-// quadrants: two warps each read the whole tile, 4 wavefronts per LDS.128 — 660 shared-memory wavefronts per 128-row
-// stage, the busiest unit of the kernel at 71 %, see profiles/README.md.)  Quadrants without columns do nothing.
+// Only the FEATURES go through the tensor core.  Round 1 sent Z~ = [X | y | 1] (34 columns at p = 32 -> N = 48, three
+// TMEM quadrants); the timeline of that kernel (profiles/r02/k2b_trace_16p16_p32.json) shows the MMA warp as the serial
+// bottleneck — 550 of 965 cycles per 128-row stage blocked in tcgen05.mma issue, i.e. the tensor pipe's per-instruction
+// time at N = 48 — with the TMEM stores of the converters and the FP64 drain of a 128 x 48 accumulator competing for
+// the same TMEM.  With A = X and B = X:  N = 32 (a third less tensor time per MMA), two quadrants instead of three
+// (a third fewer TMEM stores), and a 64 x 32 accumulator (a third of the FP64 drain).  What the targets and the ones
+// column contribute is O(p t) per row and runs on the CUDA cores of warps that hold the data anyway:
+//        X'y_j, sum x      : the converter lanes (a lane owns one feature column and has its 32 rows in registers;
+//                            y_j arrives by broadcast loads), packed f32 FMAs per stage -> f64
+//        sum y, y_j.y_k, n : 8 side lanes per target on an otherwise idle warp, f32 per box -> f64
 //
-// Two A-side shapes share the kernel:
-//   general  (q~ <= 64): A = all of Z~ (the ones column is a preset constant row of every tile), D = G~ directly;
-//   features-only (q~ > 64, p <= 64, t <= 4): A = the p feature columns, B = the tile + lo(y_j) rows + the ones/mask
-//            row, X'y = hiX.hi_y + loX.hi_y + hiX.lo_y; sum y, y_i.y_j and the row count come from side lanes in f64.
+// A-lane layout ("16 + 16"): a warp can only write the 32 TMEM lanes of its own quadrant (warp id mod 4).  Quadrant k
+// holds feature columns 16k .. 16k+15 TWICE: lanes 0..15 = hi (raw), lanes 16..31 = lo.  Lane L and lane L + 16 read
+// the SAME shared-memory address (a broadcast), so one LDS.128 of a converter warp touches 16 rows x 16 bytes = 2
+// wavefronts and every element of the tile is read from shared memory once.  Quadrants without columns do nothing.
+//
 // Data flow per CTA (persistent, one CTA per SM, 128-row stages dealt round-robin):
-//   warp 0             TMA producer  : cp.async.bulk.tensor, 4 boxes of {32 rows x q cols} per stage -> ring
+//   warp 0             TMA producer  : cp.async.bulk.tensor, per 32-row box one {32 x p} load of X and one {32 x t} of Y
 //   warp 1             MMA issuer    : 16 x tcgen05.mma (K = 8) per stage, fp32 accumulators in TMEM (double-buffered)
-//   warps 2..2+4S-1    converters    : S sets x 4 quadrant warps; tile row -> registers -> x - (x & mask) -> tcgen05.st
-//   last 8 warps       epilogue      : every 256 rows the accumulator is drained with tcgen05.ld into f64 registers
+//   warps 2..9         converters    : 2 sets x 4 quadrant warps; tile row -> registers -> x - (x & mask) -> tcgen05.st
+//   warps 10..17       epilogue      : every 256 rows the accumulator is drained with tcgen05.ld into f64 registers
 //                                      (fp32 accumulation inside the tensor core rounds toward zero: bias 1.6e-6)
 // A second tiny kernel sums the per-CTA partials in a fixed order (bit-reproducible) and applies the symmetrisation.
 // Roofline: HBM-bound, algorithmic bytes = 4 (p + t) per row (+4 with a mask).
@@ -39,7 +43,6 @@
 #include "kernels.h"
 #include <cuda.h>
 #include <cstdlib>
-#include <type_traits>
 
 namespace pdsb {
 
@@ -48,24 +51,32 @@ namespace {
 constexpr int BOX_ROWS = 32;            // K extent of one TMA box = 128 bytes of f32 = one swizzle row
 constexpr int BPS = 4;                  // boxes per pipeline stage  (stage = 128 rows)
 constexpr int STAGE_ROWS = BOX_ROWS * BPS;
-constexpr int MAX_RING = 6;             // TMA landing ring (stages)
-constexpr int MAX_AB = 3;               // TMEM A ring (slots of 128 columns)
+constexpr int MAX_RING = 10;            // TMA landing ring (stages)
+constexpr int AB = 3;                   // TMEM A ring (slots of 128 columns): 2 x 64 accumulator + 3 x 128 = 512
+constexpr int D_COLS = 64;              // TMEM columns per accumulator buffer (N <= 64)
+constexpr int A_COL0 = 2 * D_COLS;
 constexpr int FLUSH_STAGES = 2;         // accumulate 2 stages = 256 rows in fp32 (RZ accumulation) before draining to f64
+constexpr int NCONV = 2;                // converter warp sets, alternating stages
 constexpr int EPI_SETS = 2;             // epilogue warp sets, each draining half of the accumulator columns
+constexpr int NSIDE = 2;                  // side warps: warp k takes boxes 2k, 2k+1 of every stage (x . y, sum x, sum y, y . y, count)
+constexpr int NUM_WARPS = 2 + 4 * NCONV + NSIDE + 4 * EPI_SETS;
+constexpr int NUM_THREADS = NUM_WARPS * 32;     // 640 (96 registers per thread)
 constexpr int TMEM_COLS = 512;
 constexpr int A_SLOT_COLS = BPS * BOX_ROWS;
+constexpr int Y_ROWS = 8;               // tile rows reserved for the targets (t <= 4; one 8-row swizzle group)
+constexpr int MAX_T = 4;
 constexpr uint32_t HI_MASK = 0xFFFFE000u;   // TF32 keeps 10 mantissa bits
+constexpr int XSIDE_COLS = 64;          // doubles per (CTA, converter set, slot): slot j < T = x . y_j, slot T = sum x
 constexpr int YSIDE_STRIDE = 32;        // doubles per (CTA, converter set): [3u+0] sum y_u, [3u+1] sum y_u^2, [2] count, [12 + 4j + k] y_j.y_k
 
 template <int NB>
 struct Shape {
-  static constexpr int N = NB * 16;                                  // MMA N = padded number of B rows
+  static constexpr int N = NB * 16;                                  // MMA N = feature rows of the tile, padded to 16
   static constexpr int NH = N / EPI_SETS;                            // accumulator columns per epilogue set
-  static constexpr int RING = (NB == 4) ? 5 : (NB == 5 ? 4 : MAX_RING);
-  static constexpr int D_COLS = (NB <= 4) ? 64 : 80;                 // TMEM columns per accumulator buffer
-  static constexpr int AB = (NB <= 4) ? MAX_AB : 2;                  // 2 x D_COLS + AB x 128 <= 512
-  static constexpr int A_COL0 = 2 * D_COLS;
-  static constexpr uint32_t TILE_BYTES = N * 128;                    // one box-tile: N rows x 128 bytes
+  static constexpr int TILE_ROWS = N + Y_ROWS;                       // feature rows, then the target rows
+  static constexpr uint32_t TILE_BYTES = TILE_ROWS * 128;            // one box-tile
+  // ring depth: as many stages as fit in ~200 KB (the kernel is latency-bound on bytes in flight per SM)
+  static constexpr int RING = (NB == 1) ? 10 : (NB == 2 ? 10 : (NB == 3 ? 7 : 5));
   static constexpr size_t SMEM = (size_t)RING * BPS * TILE_BYTES;
 };
 
@@ -82,7 +93,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // bounded spin: a protocol bug must surface as a trapped kernel (an error the host reports), never as a hung GPU.
+  // bounded wait (4 s of %globaltimer): a protocol bug must surface as a trapped kernel (an error the host reports),
+  // never as a hung GPU.
   // First a plain non-blocking test (the phase has usually flipped long ago for the warp that is the bottleneck);
   // then try_wait with a suspend-time hint, which lets the hardware park the warp until the phase flips instead of
   // re-issuing the poll: ncu counted ~195 barrier polls per 128-row stage without it, all of them wavefronts on the
@@ -94,14 +106,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, P1;\n\t"
       "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  for (uint32_t spins = 0; !done; ++spins) {
+  if (done) return;
+  uint64_t t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!done) {
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P1;\n\t"
         "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
-    if (!done && spins > (1u << 24)) __trap();
+    if (!done) {
+      uint64_t t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 4000000000ull) __trap();          // 4 s: no legitimate wait of this kernel comes near it
+    }
   }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -168,13 +187,13 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
 }
 
 struct alignas(8) Barriers {
-  uint64_t raw_full[MAX_RING], raw_empty[MAX_RING];   // TMA landed / tile (the B operand) free again
-  uint64_t a_full[MAX_AB], a_empty[MAX_AB];           // TMEM A slot written / consumed
+  uint64_t raw_full[MAX_RING], raw_empty[MAX_RING];   // TMA landed / tile free again (MMA done with B + side lanes done)
+  uint64_t a_full[AB], a_empty[AB];                   // TMEM A slot written / consumed
   uint64_t d_full[2], d_empty[2];                     // accumulator buffer ready to drain / drained
   uint32_t tmem_base;
 };
 
-// A-side column c lives in TMEM lanes hi_lane(c) (raw) and hi_lane(c) + 16 (lo)
+// feature column c lives in TMEM lanes hi_lane(c) (raw) and hi_lane(c) + 16 (lo)
 __host__ __device__ __forceinline__ int hi_lane(int c) { return (c >> 4) * 32 + (c & 15); }
 
 #ifdef PDSB_TC_ABLATION
@@ -192,32 +211,29 @@ __device__ unsigned long long g_trace[TRACE_STAGES * TRACE_EVENTS];
 
 struct GramArgs {
   int64_t n, stages_total;
-  int q;                 // columns the TMA box brings = p + t
-  int p, t, zx, zy;      // features-only shape: feature / target rows inside the tile
-  int blocked;           // row-blocked frame (3-D tensor map) or column-major matrix (2-D)
-  int explicit_hi;       // cross-check build: the hi lanes clear the low 13 bits themselves
+  int p, t;
+  int xcol, ycol;        // row-blocked frame: first feature / target column of the frame
+  int blocked;           // row-blocked frame (3-D tensor maps) or column-major matrices (2-D)
+  int explicit_hi;       // cross-check: the hi lanes clear the low 13 bits themselves
 };
 
-// XONLY = features-only A side.  NCONV = converter sets.  DBG = timing ablations (never in production: results are
-// garbage): 1 no TMEM store, 2 no lo arithmetic, 4 no shared-memory loads, 8 no MMA.
-template <int NB, bool XONLY, int NCONV, int DBG>
-__global__ void __launch_bounds__((2 + 4 * NCONV + 4 * EPI_SETS) * 32, 1)
-gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ mask, const GramArgs g,
-                    double* __restrict__ partials /* [grid][128][N] */, double* __restrict__ yside /* [grid][NCONV][32] */) {
+// T = targets the side lanes are compiled for (1, or 4 for t = 2..4).  DBG = timing ablations (never in production:
+// results are garbage): 1 no TMEM store, 2 no lo arithmetic, 4 no shared-memory loads, 8 no MMA, 16 timeline trace.
+template <int NB, int T, int DBG>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
+                    const float* __restrict__ mask, const GramArgs g, double* __restrict__ partials /* [grid][128][N] */,
+                    double* __restrict__ xside /* [grid][NSIDE][T+1][64] */, double* __restrict__ yside /* [grid][NSIDE][32] */) {
   using S = Shape<NB>;
-  constexpr int N = S::N, NH = S::NH, RING = S::RING, AB = S::AB;
+  constexpr int N = S::N, NH = S::NH, RING = S::RING;
   constexpr uint32_t TILE_BYTES = S::TILE_BYTES;
-  constexpr int NTHREADS = (2 + 4 * NCONV + 4 * EPI_SETS) * 32;
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* raw = smem;                                              // RING * BPS * TILE_BYTES
+  unsigned char* raw = smem;                              // RING * BPS * TILE_BYTES
   Barriers* bars = reinterpret_cast<Barriers*>(raw + S::SMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = g.q;
-  const int ncols_a = XONLY ? g.p : q + 1;                // columns on the A side
-  const int nact = (ncols_a + 15) >> 4;                   // TMEM quadrants that hold columns
-  const bool side_own_warp = XONLY && nact < 4;           // y / ones side work on an otherwise idle quadrant warp
-  const int row_ones = XONLY ? q + g.t : q;               // constant 1.0 row of every tile (B operand; A lane when !XONLY)
+  const int p = g.p, t = g.t;
+  const int nact = (p + 15) >> 4;                         // TMEM quadrants that hold feature columns
   // stages are dealt round-robin: at any moment the CTAs stream ADJACENT rows of every column (DRAM page locality:
   // with one contiguous range per CTA the chip ran 148 x q far-apart 128-byte streams and topped out at 4.3 TB/s
   // even with all arithmetic removed)
@@ -226,18 +242,20 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
   auto stage_row0 = [&](uint32_t it) { return ((int64_t)it * gridDim.x + blockIdx.x) * STAGE_ROWS; };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < RING; ++i) { mbar_init(&bars->raw_full[i], 1); mbar_init(&bars->raw_empty[i], 1); }
-    for (int i = 0; i < AB; ++i) { mbar_init(&bars->a_full[i], nact + (side_own_warp ? 1 : 0)); mbar_init(&bars->a_empty[i], 1); }
+    for (int i = 0; i < RING; ++i) { mbar_init(&bars->raw_full[i], 1); mbar_init(&bars->raw_empty[i], 1 + NSIDE); }   // the MMA's commit + the side warps
+    for (int i = 0; i < AB; ++i) { mbar_init(&bars->a_full[i], nact); mbar_init(&bars->a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->d_full[i], 1); mbar_init(&bars->d_empty[i], nact * EPI_SETS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // rows >= q of every tile are never written by the TMA (its box has q rows): the ones row is preset to 1.0, all others
-  // (zero padding, lo(y) rows until the side lanes write them) to 0 — position-independent under the swizzle
-  for (int i = threadIdx.x; i < RING * BPS * (N - q) * 8; i += NTHREADS) {
-    const int tile = i / ((N - q) * 8), rem = i % ((N - q) * 8);
-    const int r = q + rem / 8, c = rem % 8;
-    const uint32_t val = (r == row_ones) ? 0x3F800000u : 0u;
-    *reinterpret_cast<uint4*>(raw + (size_t)tile * TILE_BYTES + (size_t)r * 128 + c * 16) = make_uint4(val, val, val, val);
+  // rows the TMA never writes (feature rows p .. N-1 feed accumulator columns nobody reads, target rows t .. 7 feed
+  // side lanes whose results nobody reads): zero them once so that nothing uninitialised is ever multiplied
+  for (int i = threadIdx.x; i < RING * BPS * (S::TILE_ROWS - p - t) * 8; i += NUM_THREADS) {
+    const int per = (S::TILE_ROWS - p - t) * 8;
+    const int tile = i / per, rem = i % per;
+    int r = rem / 8;
+    const int c = rem % 8;
+    r = (r < N - p) ? p + r : N + t + (r - (N - p));
+    *reinterpret_cast<uint4*>(raw + (size_t)tile * TILE_BYTES + (size_t)r * 128 + c * 16) = make_uint4(0, 0, 0, 0);
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS));
@@ -256,13 +274,18 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
       mbar_wait(&bars->raw_empty[rs], ph ^ 1);
       PDSB_TRACE(it, 0);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&bars->raw_full[rs], (uint32_t)(BPS * q * 128));
+        mbar_arrive_expect_tx(&bars->raw_full[rs], (uint32_t)(BPS * (p + t) * 128));
         const int64_t row0 = stage_row0(it);
 #pragma unroll
         for (int b = 0; b < BPS; ++b) {
-          void* dst = raw + ((size_t)rs * BPS + b) * TILE_BYTES;
-          if (g.blocked) tma_load_3d(dst, &tmap, &bars->raw_full[rs], b * BOX_ROWS, 0, (int)(row0 / STAGE_ROWS));
-          else tma_load_2d(dst, &tmap, &bars->raw_full[rs], (int)(row0 + b * BOX_ROWS), 0);
+          unsigned char* dst = raw + ((size_t)rs * BPS + b) * TILE_BYTES;
+          if (g.blocked) {
+            tma_load_3d(dst, &tmap_x, &bars->raw_full[rs], b * BOX_ROWS, g.xcol, (int)(row0 / STAGE_ROWS));
+            tma_load_3d(dst + N * 128, &tmap_y, &bars->raw_full[rs], b * BOX_ROWS, g.ycol, (int)(row0 / STAGE_ROWS));
+          } else {
+            tma_load_2d(dst, &tmap_x, &bars->raw_full[rs], (int)(row0 + b * BOX_ROWS), 0);
+            tma_load_2d(dst + N * 128, &tmap_y, &bars->raw_full[rs], (int)(row0 + b * BOX_ROWS), 0);
+          }
         }
       }
       __syncwarp();
@@ -282,8 +305,8 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
       tc_fence_after();
       PDSB_TRACE(it, 6);
       if (elect_one()) {
-        const uint32_t d_addr = tmem + buf * S::D_COLS;
-        const uint32_t a_base = tmem + S::A_COL0 + s * A_SLOT_COLS;
+        const uint32_t d_addr = tmem + buf * D_COLS;
+        const uint32_t a_base = tmem + A_COL0 + s * A_SLOT_COLS;
         const uint64_t bd0 = make_b_desc(raw_addr + rs * (BPS * TILE_BYTES));
         if (!(DBG & 8)) {
 #pragma unroll
@@ -297,7 +320,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
           }
         }
         tc_commit(&bars->a_empty[s]);       // TMEM A slot reusable
-        tc_commit(&bars->raw_empty[rs]);    // tile (B operand) reusable
+        tc_commit(&bars->raw_empty[rs]);    // tile (B operand) reusable once the side lanes have arrived too
         if (fl == FLUSH_STAGES - 1 || it == my_stages - 1) tc_commit(&bars->d_full[buf]);
       }
       __syncwarp();
@@ -308,32 +331,28 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
     }
   } else if (warp < 2 + 4 * NCONV) {
     // =============================== converters: NCONV sets x 4 quadrant warps; set j owns stages it = j (mod NCONV) ===
+    // tile row -> registers -> hi / lo -> tcgen05.st, nothing else: the stage rate of the kernel is set by its slowest warp
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
     const uint32_t set = (uint32_t)(warp - 2) >> 2;
-    const bool do_x = quad < nact;
-    const bool do_side = XONLY && (side_own_warp ? quad == nact : quad == 0);
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    if (!do_x && set == 0) {
+    if (quad >= nact) {
       // lanes nobody feeds: zero them once so the MMA never multiplies uninitialised TMEM (their accumulator rows are
       // not read either way)
-      uint32_t z[32];
+      if (set == 0) {
+        uint32_t z[32];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) z[k] = 0u;
-      for (int c = 0; c < AB * BPS; ++c) tmem_st32(tmem + lane_addr + (uint32_t)(S::A_COL0 + c * BOX_ROWS), z);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    if (do_x || do_side) {
-      const int m = quad * 16 + (lane & 15);     // A-side column of this lane (lanes L and L + 16 share it)
-      const bool is_data = do_x && m < (XONLY ? g.p : q);
-      const bool is_ones = !XONLY && do_x && m == q;
+        for (int k = 0; k < 32; ++k) z[k] = 0u;
+        for (int c = 0; c < AB * BPS; ++c) tmem_st32(tmem + lane_addr + (uint32_t)(A_COL0 + c * BOX_ROWS), z);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+    } else {
+      const int m = quad * 16 + (lane & 15);     // feature column of this lane (lanes L and L + 16 share it)
       // padding lanes feed accumulator rows nobody reads: they load the same address as a real lane (a broadcast)
-      const int trow = XONLY ? g.zx + (m < g.p ? m : 0) : (m < q ? m : q);
+      const int trow = m < p ? m : 0;
       const uint32_t sw = (uint32_t)(trow & 7);
-      // hi lanes keep the raw value (x - 0), lo lanes hold x - (x & HI_MASK): one AND + one FADD per element, no select
+      // hi lanes keep the raw value (x - 0), lo lanes hold x - (x & HI_MASK): one LOP3 per element, one FADD2 per two
       // (cross-check build: the hi lanes subtract their own low 13 bits, i.e. hold trunc(x) explicitly)
       const uint32_t sub_mask = (lane & 16) ? HI_MASK : (g.explicit_hi ? ~HI_MASK : 0u);
-      float sy = 0.0f, syy = 0.0f, sxy[3] = {0.0f, 0.0f, 0.0f};   // sxy[d-1]: y_j . y_{j+d} (multi-target cross moments)
-      double dsy = 0.0, dsyy = 0.0, dcnt = 0.0, dxy[3] = {0.0, 0.0, 0.0};
       for (uint32_t it = set; it < my_stages; it += NCONV) {
         const uint32_t rs = it % RING, rph = (it / RING) & 1;
         const uint32_t s = it % AB, sph = (it / AB) & 1;
@@ -342,137 +361,166 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
         mbar_wait(&bars->a_empty[s], sph ^ 1);
         tc_fence_after();
         if (quad == 0) PDSB_TRACE(it, 3);
-        const int64_t row0 = stage_row0(it);
-        const int64_t left64 = g.n - row0;
-        const int left = left64 > STAGE_ROWS ? STAGE_ROWS : (int)left64;     // valid rows in this stage (>= 1)
-        const bool fast = (mask == nullptr) && (left == STAGE_ROWS);          // warp-uniform
-        // the four boxes of the stage; instantiated twice so that the common case (no mask, full stage) is straight-line
-        auto convert_stage = [&](auto fast_tag) {
-        constexpr bool FAST = decltype(fast_tag)::value;
 #pragma unroll
         for (int b = 0; b < BPS; ++b) {
-          unsigned char* tile = raw + ((size_t)rs * BPS + b) * TILE_BYTES;
           uint32_t v[32];
-          if (do_x) {
-            const unsigned char* rowp = tile + (size_t)trow * 128;
+          const unsigned char* rowp = raw + ((size_t)rs * BPS + b) * TILE_BYTES + (size_t)trow * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              uint4 x = make_uint4(c, c + 1, c + 2, c + 3);
-              if (!(DBG & 4)) x = *reinterpret_cast<const uint4*>(rowp + ((c ^ sw) << 4));
-              v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+          for (int c = 0; c < 8; ++c) {
+            uint4 x = make_uint4(c, c + 1, c + 2, c + 3);
+            if (!(DBG & 4)) x = *reinterpret_cast<const uint4*>(rowp + ((c ^ sw) << 4));
+            v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+          }
+          if (!(DBG & 2)) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) {
+              // -(x & mask) as one LOP3: (x & mask) ^ sign   (hi lanes: x + (-0) = x; lo lanes: exact in fp32)
+              const float2 r = __fadd2_rn(make_float2(__uint_as_float(v[k]), __uint_as_float(v[k + 1])),
+                                          make_float2(__uint_as_float((v[k] & sub_mask) ^ 0x80000000u),
+                                                      __uint_as_float((v[k + 1] & sub_mask) ^ 0x80000000u)));
+              v[k] = __float_as_uint(r.x); v[k + 1] = __float_as_uint(r.y);
             }
           }
-          if (!XONLY && !FAST) {
-            // masked / ragged stage: the ones column differs from the preset constant.  The hi "ones" lane writes the
-            // actual values to its A lane and to row q of the tile (the B operand); tiles are reused, so a kernel with a
-            // mask takes this path for every stage and always rewrites row q.
-            const int nvalid = left - b * BOX_ROWS;
-            float mk = 0.0f;
-            if (lane < nvalid) mk = mask ? __ldg(mask + row0 + b * BOX_ROWS + lane) : 1.0f;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const uint32_t o = __float_as_uint(__shfl_sync(0xffffffffu, mk, k));
-              v[k] = is_data ? v[k] : (is_ones ? o : 0u);
-            }
-            if (is_ones && !(lane & 16)) {
-              unsigned char* rowp = tile + (size_t)q * 128;
-#pragma unroll
-              for (int c = 0; c < 8; ++c)
-                *reinterpret_cast<uint4*>(rowp + ((c ^ sw) << 4)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-            }
-          }
-          if (XONLY && do_side) {               // warp-uniform
-            // 8 lanes per target: lane 8j + c handles the c-th 16-byte chunk of y_j's row (lo(y) row, sum y, sum y^2)
-            if (lane < 8 * g.t) {
-              const int j = lane >> 3, c = lane & 7;
-              const int yr = g.zy + j, lr = q + j;
-              const uint4 yv = *reinterpret_cast<const uint4*>(tile + (size_t)yr * 128 + ((c ^ (yr & 7)) << 4));
-              const float y0 = __uint_as_float(yv.x), y1 = __uint_as_float(yv.y), y2 = __uint_as_float(yv.z), y3 = __uint_as_float(yv.w);
-              uint4 lo;
-              lo.x = __float_as_uint(y0 - __uint_as_float(yv.x & HI_MASK));
-              lo.y = __float_as_uint(y1 - __uint_as_float(yv.y & HI_MASK));
-              lo.z = __float_as_uint(y2 - __uint_as_float(yv.z & HI_MASK));
-              lo.w = __float_as_uint(y3 - __uint_as_float(yv.w & HI_MASK));
-              *reinterpret_cast<uint4*>(tile + (size_t)lr * 128 + ((c ^ (lr & 7)) << 4)) = lo;
-              sy += (y0 + y1) + (y2 + y3);
-              syy = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, syy))));
-#pragma unroll
-              for (int d = 1; d < 4; ++d)
-                if (j + d < g.t) {
-                  const int kr = g.zy + j + d;
-                  const uint4 kv = *reinterpret_cast<const uint4*>(tile + (size_t)kr * 128 + ((c ^ (kr & 7)) << 4));
-                  sxy[d - 1] = fmaf(y0, __uint_as_float(kv.x), fmaf(y1, __uint_as_float(kv.y),
-                               fmaf(y2, __uint_as_float(kv.z), fmaf(y3, __uint_as_float(kv.w), sxy[d - 1]))));
-                }
-            }
-            if (!FAST) {
-              // masked / ragged stage: lanes 0..7 rewrite the ones row with the 32 mask values of this box
-              const int nvalid = left - b * BOX_ROWS;
-              if (lane < 8) {
-                float o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int k = lane * 4 + e;
-                  o[e] = (k < nvalid) ? (mask ? __ldg(mask + row0 + b * BOX_ROWS + k) : 1.0f) : 0.0f;
-                }
-                dcnt += (double)((o[0] + o[1]) + (o[2] + o[3]));
-                *reinterpret_cast<uint4*>(tile + (size_t)row_ones * 128 + ((lane ^ (row_ones & 7)) << 4)) =
-                    make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
-              }
-            }
-          }
-          if (do_x) {
-            if (!(DBG & 2)) {
-#pragma unroll
-              for (int k = 0; k < 32; k += 2) {           // one AND per element, one packed subtract per two (FADD2)
-                // -(x & mask) as one LOP3: (x & mask) ^ sign   (hi lanes: x + (-0) = x)
-                const float2 r = __fadd2_rn(make_float2(__uint_as_float(v[k]), __uint_as_float(v[k + 1])),
-                                            make_float2(__uint_as_float((v[k] & sub_mask) ^ 0x80000000u),
-                                                        __uint_as_float((v[k + 1] & sub_mask) ^ 0x80000000u)));
-                v[k] = __float_as_uint(r.x); v[k + 1] = __float_as_uint(r.y);     // hi: x - 0 = x; lo: exact in fp32
-              }
-            }
-            if (!(DBG & 1)) tmem_st32(tmem + lane_addr + (uint32_t)(S::A_COL0 + s * A_SLOT_COLS + b * BOX_ROWS), v);
-            else if (v[0] == 0x7fc12345u && v[31] == 0x12345u) bars->tmem_base = v[5];   // ablation build: keep v alive
-          }
-        }
-        };
-        if (fast) convert_stage(std::true_type{}); else convert_stage(std::false_type{});
-        if (XONLY && do_side) {
-          dsy += (double)sy; dsyy += (double)syy; sy = 0.0f; syy = 0.0f;
-#pragma unroll
-          for (int d = 0; d < 3; ++d) { dxy[d] += (double)sxy[d]; sxy[d] = 0.0f; }
+          if (!(DBG & 1)) tmem_st32(tmem + lane_addr + (uint32_t)(A_COL0 + s * A_SLOT_COLS + b * BOX_ROWS), v);
+          else if (v[0] == 0x7fc12345u && v[31] == 0x12345u) bars->tmem_base = v[5];   // ablation build: keep v alive
         }
         if (quad == 0) PDSB_TRACE(it, 4);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        if (XONLY ? do_side : !fast) fence_async_smem();   // tile rows written through the generic proxy -> tensor core
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->a_full[s]);
         if (quad == 0) PDSB_TRACE(it, 5);
       }
-      if (XONLY && do_side) {
-        // reduce the 8 chunk-lanes of every target (fixed order -> reproducible) and the masked-row count
-        double* ys = yside + ((size_t)blockIdx.x * NCONV + set) * YSIDE_STRIDE;
-        for (int off = 4; off; off >>= 1) {
-          dsy += __shfl_down_sync(0xffffffffu, dsy, off, 8);
-          dsyy += __shfl_down_sync(0xffffffffu, dsyy, off, 8);
-          dcnt += __shfl_down_sync(0xffffffffu, dcnt, off, 8);
+    }
+  } else if (warp < 2 + 4 * NCONV + NSIDE) {
+    // =============================== side warps: warp k takes boxes 2k, 2k+1 of EVERY stage =======================
+    // lane = feature (two per lane when p > 32):  x . y_j and sum x in packed f32 (four independent chains per slot, one
+    // f64 flush per stage);  lanes 8j .. 8j+7 also hold the c-th 16-byte chunk of target j: sum y, y_j . y_k;  lanes 0..7
+    // count the rows of a masked frame.  All of it reads the tile only, so the warp releases the tile itself.
+    constexpr int NF = (NB >= 3) ? 2 : 1;      // features per lane
+    const int sw_id = warp - (2 + 4 * NCONV);
+    int frow[NF];
+    uint32_t fsw[NF];
 #pragma unroll
-          for (int d = 0; d < 3; ++d) dxy[d] += __shfl_down_sync(0xffffffffu, dxy[d], off, 8);
-        }
-        if ((lane & 7) == 0 && (lane >> 3) < g.t) {
-          const int j = lane >> 3;
-          ys[j * 3 + 0] = dsy; ys[j * 3 + 1] = dsyy;
-          for (int d = 1; d < 4; ++d) if (j + d < g.t) ys[12 + j * 4 + (j + d)] = dxy[d - 1];
-        }
-        if (lane == 0) ys[2] = dcnt;
+    for (int f = 0; f < NF; ++f) { const int m = lane + 32 * f; frow[f] = m < p ? m : 0; fsw[f] = (uint32_t)(frow[f] & 7); }
+    double dxs[NF][T + 1];                                        // f64: x . y_j (j < T), sum x
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+#pragma unroll
+      for (int j = 0; j <= T; ++j) dxs[f][j] = 0.0;
+    double dsy = 0.0, dsyy = 0.0, dcnt = 0.0, dxy[3] = {0.0, 0.0, 0.0};
+    uint32_t rs = 0, rph = 0;
+    for (uint32_t it = 0; it < my_stages; ++it) {
+      mbar_wait(&bars->raw_full[rs], rph);
+      // packed f32 over NATURAL register pairs: a 16-byte load gives rows (4c, 4c+1) and (4c+2, 4c+3) of a column, the
+      // broadcast load of y_j the same rows of the target -> x . y and sum x cost one FFMA2 / FADD2 per two rows, no moves.
+      // Two independent chains per sum (the two pairs of a chunk); one f64 flush per stage (64-term f32 sums, RN).
+      float2 axy[NF][T][2], asx[NF][2];
+      float sy = 0.0f, syy = 0.0f, sxy[3] = {0.0f, 0.0f, 0.0f};   // lanes 8j + c: chunk c of target j; sxy[d-1] = y_j . y_{j+d}
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+#pragma unroll
+        for (int j = 0; j < T; ++j) axy[f][j][0] = axy[f][j][1] = make_float2(0.0f, 0.0f);
+        asx[f][0] = asx[f][1] = make_float2(0.0f, 0.0f);
       }
+#pragma unroll
+      for (int bb = 0; bb < BPS / NSIDE; ++bb) {
+      const int b = sw_id * (BPS / NSIDE) + bb;
+      const unsigned char* tile = raw + ((size_t)rs * BPS + b) * TILE_BYTES;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float2 y01[T], y23[T];
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+          const uint4 yv = *reinterpret_cast<const uint4*>(tile + (size_t)(N + j) * 128 + ((c ^ j) << 4));   // same address in every lane
+          y01[j] = make_float2(__uint_as_float(yv.x), __uint_as_float(yv.y));
+          y23[j] = make_float2(__uint_as_float(yv.z), __uint_as_float(yv.w));
+        }
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          const uint4 xv = *reinterpret_cast<const uint4*>(tile + (size_t)frow[f] * 128 + ((c ^ fsw[f]) << 4));
+          const float2 x01 = make_float2(__uint_as_float(xv.x), __uint_as_float(xv.y));
+          const float2 x23 = make_float2(__uint_as_float(xv.z), __uint_as_float(xv.w));
+#pragma unroll
+          for (int j = 0; j < T; ++j) {
+            axy[f][j][0] = __ffma2_rn(x01, y01[j], axy[f][j][0]);
+            axy[f][j][1] = __ffma2_rn(x23, y23[j], axy[f][j][1]);
+          }
+          asx[f][0] = __fadd2_rn(asx[f][0], x01);
+          asx[f][1] = __fadd2_rn(asx[f][1], x23);
+        }
+      }
+      if (lane < 8 * t) {
+        const int j = lane >> 3, c = lane & 7;
+        const uint4 yv = *reinterpret_cast<const uint4*>(tile + (size_t)(N + j) * 128 + ((c ^ j) << 4));
+        const float y0 = __uint_as_float(yv.x), y1 = __uint_as_float(yv.y), y2 = __uint_as_float(yv.z), y3 = __uint_as_float(yv.w);
+        sy += (y0 + y1) + (y2 + y3);                                   // 8 values per lane and stage in f32, then f64
+        syy = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, syy))));
+        if (T > 1) {
+#pragma unroll
+          for (int d = 1; d < 4; ++d)
+            if (j + d < t) {
+              const int kr = j + d;
+              const uint4 kv = *reinterpret_cast<const uint4*>(tile + (size_t)(N + kr) * 128 + ((c ^ kr) << 4));
+              sxy[d - 1] = fmaf(y0, __uint_as_float(kv.x), fmaf(y1, __uint_as_float(kv.y),
+                           fmaf(y2, __uint_as_float(kv.z), fmaf(y3, __uint_as_float(kv.w), sxy[d - 1]))));
+            }
+        }
+      }
+      if (mask != nullptr && lane < 8) {
+        // row count of a masked frame: the packer zeroes masked rows, so only the count needs the mask
+        const int64_t r0 = stage_row0(it) + b * BOX_ROWS + lane * 4;
+        float o = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (r0 + e < g.n) o += __ldg(mask + r0 + e);
+        dcnt += (double)o;
+      }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->raw_empty[rs]);           // the MMA's commit is the other arrival
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+#pragma unroll
+        for (int j = 0; j < T; ++j) { const float2 a = __fadd2_rn(axy[f][j][0], axy[f][j][1]); dxs[f][j] += (double)(a.x + a.y); }
+        const float2 a = __fadd2_rn(asx[f][0], asx[f][1]);
+        dxs[f][T] += (double)(a.x + a.y);
+      }
+      dsy += (double)sy; dsyy += (double)syy;
+      if (T > 1) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dxy[d] += (double)sxy[d];
+      }
+      if (++rs == RING) { rs = 0; rph ^= 1; }
+    }
+    {
+      double* xs = xside + ((size_t)blockIdx.x * NSIDE + sw_id) * (T + 1) * XSIDE_COLS;
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const int m = lane + 32 * f;
+        if (m < p)
+#pragma unroll
+          for (int j = 0; j <= T; ++j) xs[j * XSIDE_COLS + m] = dxs[f][j];
+      }
+      // reduce the 8 chunk-lanes of every target (fixed order -> reproducible) and the masked-row count
+      double* ys = yside + ((size_t)blockIdx.x * NSIDE + sw_id) * YSIDE_STRIDE;
+      for (int off = 4; off; off >>= 1) {
+        dsy += __shfl_down_sync(0xffffffffu, dsy, off, 8);
+        dsyy += __shfl_down_sync(0xffffffffu, dsyy, off, 8);
+        dcnt += __shfl_down_sync(0xffffffffu, dcnt, off, 8);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dxy[d] += __shfl_down_sync(0xffffffffu, dxy[d], off, 8);
+      }
+      if ((lane & 7) == 0 && (lane >> 3) < t) {
+        const int j = lane >> 3;
+        ys[j * 3 + 0] = dsy; ys[j * 3 + 1] = dsyy;
+        for (int d = 1; d < 4; ++d) if (j + d < t) ys[12 + j * 4 + (j + d)] = dxy[d - 1];
+      }
+      if (lane == 0) ys[2] = dcnt;
     }
   } else {
     // =============================== epilogue: EPI_SETS x 4 warps, set e drains columns [e*NH, (e+1)*NH) =========
     const int quad = warp & 3;
-    const int eset = (warp - (2 + 4 * NCONV)) >> 2;
+    const int eset = (warp - (2 + 4 * NCONV + NSIDE)) >> 2;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     if (quad < nact) {
       double acc[NH];
@@ -484,32 +532,17 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
         mbar_wait(&bars->d_full[buf], dph);
         tc_fence_after();
         if (quad == 0 && eset == 0) PDSB_TRACE(grp * FLUSH_STAGES + FLUSH_STAGES - 1, 8);
-        if constexpr (NB <= 4) {
-          uint32_t v[NH];
+        uint32_t v[NH];
 #pragma unroll
-          for (int c = 0; c < NH / 8; ++c) tmem_ld8(tmem + lane_addr + (uint32_t)(buf * S::D_COLS + eset * NH + c * 8), v + 8 * c);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->d_empty[buf]);      // the buffer is free before the f64 adds run
-          if (quad == 0 && eset == 0) PDSB_TRACE(grp * FLUSH_STAGES + FLUSH_STAGES - 1, 9);
+        for (int c = 0; c < NH / 8; ++c) tmem_ld8(tmem + lane_addr + (uint32_t)(buf * D_COLS + eset * NH + c * 8), v + 8 * c);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->d_empty[buf]);      // the buffer is free before the f64 adds run
+        if (quad == 0 && eset == 0) PDSB_TRACE(grp * FLUSH_STAGES + FLUSH_STAGES - 1, 9);
 #pragma unroll
-          for (int j = 0; j < NH; ++j) acc[j] += (double)__uint_as_float(v[j]);
-          if (quad == 0 && eset == 0) PDSB_TRACE(grp * FLUSH_STAGES + FLUSH_STAGES - 1, 10);
-        } else {
-          // N = 80: drain in chunks of 8 columns (keeps the register footprint flat)
-#pragma unroll
-          for (int c = 0; c < NH / 8; ++c) {
-            uint32_t v[8];
-            tmem_ld8(tmem + lane_addr + (uint32_t)(buf * S::D_COLS + eset * NH + c * 8), v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[c * 8 + j] += (double)__uint_as_float(v[j]);
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->d_empty[buf]);
-        }
+        for (int j = 0; j < NH; ++j) acc[j] += (double)__uint_as_float(v[j]);
+        if (quad == 0 && eset == 0) PDSB_TRACE(grp * FLUSH_STAGES + FLUSH_STAGES - 1, 10);
         if (buf) dph ^= 1;
         buf ^= 1;
       }
@@ -527,68 +560,30 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
   }
 }
 
-// Sum the per-CTA partials in a fixed order, then  G~[a][b] = HH[a][b] + LH[a][b] + LH[b][a]  and permute the Z~
-// columns (targets may precede the features in memory) into the moments order [X | Y | 1].
-__global__ void gram_finalize_kernel(const double* __restrict__ partials, int nparts, int N, int p, int t, int zx, int zy,
-                                     double* __restrict__ M) {
-  // one warp per output element of the upper triangle: lane l sums parts l, l+32, ... then a fixed-order xor tree
-  // (bit-reproducible); the mirrored element gets the same value -> exactly symmetric
-  const int q1 = p + t + 1;
-  const int lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (idx >= q1 * q1) return;
-  const int i = idx / q1, j = idx % q1;
-  if (i > j) return;
-  auto zcol = [&](int c) { return c < p ? zx + c : (c < p + t ? zy + (c - p) : p + t); };
-  const int a = zcol(i), b = zcol(j);
-  const int la = hi_lane(a), lb = hi_lane(b);
-  double hh = 0.0, hh_t = 0.0, lh_ab = 0.0, lh_ba = 0.0;
-  for (int k = lane; k < nparts; k += 32) {
-    const double* P = partials + (size_t)k * 128 * N;
-    hh += P[(size_t)la * N + b];
-    hh_t += P[(size_t)lb * N + a];
-    lh_ab += P[(size_t)(la + 16) * N + b];
-    lh_ba += P[(size_t)(lb + 16) * N + a];
-  }
-  for (int off = 16; off; off >>= 1) {
-    hh += __shfl_xor_sync(0xffffffffu, hh, off);
-    hh_t += __shfl_xor_sync(0xffffffffu, hh_t, off);
-    lh_ab += __shfl_xor_sync(0xffffffffu, lh_ab, off);
-    lh_ba += __shfl_xor_sync(0xffffffffu, lh_ba, off);
-  }
-  if (lane == 0) {
-    const double r = 0.5 * (hh + hh_t) + (lh_ab + lh_ba);
-    M[(size_t)i * q1 + j] = r;
-    M[(size_t)j * q1 + i] = r;
-  }
-}
-
-// finalize for the features-only shape: moments order [X | Y | 1]
-__global__ void gram_finalize_xonly_kernel(const double* __restrict__ partials, const double* __restrict__ yside, int nparts,
-                                           int nconv, int N, int p, int t, int zx, int zy, int64_t n, int masked,
-                                           double* __restrict__ M) {
+// Sum the per-CTA partials in a fixed order (bit-reproducible), X'X[a][b] = HH[a][b] + LH[a][b] + LH[b][a], and lay the
+// moments out in the order [X | Y | 1].  One thread per element of the upper triangle, mirrored -> exactly symmetric.
+__global__ void gram_finalize_kernel(const double* __restrict__ partials, const double* __restrict__ xside,
+                                     const double* __restrict__ yside, int nparts, int N, int T, int p, int t, int64_t n,
+                                     int masked, double* __restrict__ M) {
   const int q1 = p + t + 1;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= q1 * q1) return;
   int i = idx / q1, j = idx % q1;
-  if (i > j) { int x = i; i = j; j = x; }          // evaluate the upper triangle, mirror -> exactly symmetric
-  const int q = p + t;
+  if (i > j) return;
   auto sum_d = [&](int lanei, int col) { double s = 0.0; for (int k = 0; k < nparts; ++k) s += partials[((size_t)k * 128 + lanei) * N + col]; return s; };
   double r;
   if (j < p) {                                     // X'X
-    const int a = i, b = j;
-    const double hh = 0.5 * (sum_d(hi_lane(a), zx + b) + sum_d(hi_lane(b), zx + a));
-    r = hh + sum_d(hi_lane(a) + 16, zx + b) + sum_d(hi_lane(b) + 16, zx + a);
-  } else if (i < p && j < p + t) {                 // X'y
-    const int a = i, k = j - p;
-    r = sum_d(hi_lane(a), zy + k) + sum_d(hi_lane(a) + 16, zy + k) + sum_d(hi_lane(a), q + k) + sum_d(hi_lane(a) + 16, q + k);
-  } else if (i < p) {                              // column sums (ones / mask row)
-    r = sum_d(hi_lane(i), q + t) + sum_d(hi_lane(i) + 16, q + t);
+    const double hh = 0.5 * (sum_d(hi_lane(i), j) + sum_d(hi_lane(j), i));
+    r = hh + sum_d(hi_lane(i) + 16, j) + sum_d(hi_lane(j) + 16, i);
+  } else if (i < p) {                              // X'y_k (slot k) and the column sums (slot T) from the converter lanes
+    const int slot = (j < p + t) ? j - p : T;
+    r = 0.0;
+    for (int k = 0; k < nparts * NSIDE; ++k) r += xside[((size_t)k * (T + 1) + slot) * XSIDE_COLS + i];
   } else {
-    // y / ones block from the side accumulators
-    double sy[4] = {0, 0, 0, 0}, syy[4] = {0, 0, 0, 0}, cnt = 0.0, cross = 0.0;
+    // y / ones block from the side lanes
+    double sy[MAX_T] = {0, 0, 0, 0}, syy[MAX_T] = {0, 0, 0, 0}, cnt = 0.0, cross = 0.0;
     const bool want_cross = (j < p + t) && (i != j);
-    for (int k = 0; k < nparts * nconv; ++k) {
+    for (int k = 0; k < nparts * NSIDE; ++k) {
       const double* ys = yside + (size_t)k * YSIDE_STRIDE;
       for (int u = 0; u < t; ++u) { sy[u] += ys[u * 3 + 0]; syy[u] += ys[u * 3 + 1]; }
       cnt += ys[2];
@@ -596,7 +591,7 @@ __global__ void gram_finalize_xonly_kernel(const double* __restrict__ partials, 
     }
     const double count = masked ? cnt : (double)n;
     if (j == p + t) r = (i == p + t) ? count : sy[i - p];
-    else r = (i == j) ? syy[i - p] : cross;         // y_i . y_j from the side lanes (exact products, f64 across stages)
+    else r = (i == j) ? syy[i - p] : cross;         // y_i . y_j (exact products, f64 across stages)
   }
   M[(size_t)i * q1 + j] = r;
   M[(size_t)j * q1 + i] = r;
@@ -618,27 +613,9 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// geometry shared by the support check and the launcher
-struct Geometry { const float* base; int q; int zx, zy; bool ok; bool blocked; };
+bool shape_ok(int p, int t) { return p >= 1 && p <= 64 && t >= 1 && t <= MAX_T; }
 
-bool shape_ok(int p, int t) {
-  if (p < 1 || t < 1 || p > 64 || t > 8) return false;
-  if (p + t + 1 <= 64) return true;                       // general shape
-  return p + 2 * t + 1 <= 80 && t <= 4;                   // features-only shape
-}
-
-Geometry analyse(const float* X, int64_t ldx, const float* Y, int64_t ldy, int p, int t) {
-  Geometry g{nullptr, p + t, 0, 0, false, false};
-  if (!shape_ok(p, t)) return g;
-  if (ldx != ldy || (ldx % 4) != 0) return g;
-  if (Y == X + (size_t)p * ldx) { g.base = X; g.zx = 0; g.zy = p; g.ok = true; }          // [X | Y]
-  else if (X == Y + (size_t)t * ldy) { g.base = Y; g.zx = t; g.zy = 0; g.ok = true; }     // [Y | X]
-  if (g.ok && (reinterpret_cast<uintptr_t>(g.base) & 15)) g.ok = false;
-  return g;
-}
-
-// 1 (default): general shape whenever q~ <= 64;  3: features-only A side for every shape it supports (cross-check);
-// 0: general shape with the hi lanes clearing the low 13 bits themselves (proves the hardware truncation of A).
+// 1 (default): raw hi operand;  0: the hi lanes clear the low 13 bits themselves (proves the hardware truncation of A)
 std::atomic<int> g_tc_mode{-1};
 int tc_mode() {
   int m = g_tc_mode.load();
@@ -649,45 +626,115 @@ int tc_mode() {
   }
   return m;
 }
-int conv_sets() {
-  static int v = [] { const char* e = getenv("PDSB_TC_NCONV"); const int x = e ? atoi(e) : 2; return (x == 3) ? 3 : 2; }();
-  return v;
-}
 
-template <int NB, bool XONLY, int NCONV, int DBG>
-int launch_one(const CUtensorMap& tmap, const float* mask, const GramArgs& g, int grid, double* partials, double* yside,
-               cudaStream_t s) {
+template <int NB, int T, int DBG>
+int launch_one(const CUtensorMap& tx, const CUtensorMap& ty, const float* mask, const GramArgs& g, int grid,
+               double* partials, double* xside, double* yside, cudaStream_t s) {
   const size_t smem = Shape<NB>::SMEM + sizeof(Barriers) + 256;
-  auto k = gram_tcgen05_kernel<NB, XONLY, NCONV, DBG>;
+  auto k = gram_tcgen05_kernel<NB, T, DBG>;
   PDSB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<grid, (2 + 4 * NCONV + 4 * EPI_SETS) * 32, smem, s>>>(tmap, mask, g, partials, yside);
+  k<<<grid, NUM_THREADS, smem, s>>>(tx, ty, mask, g, partials, xside, yside);
   PDSB_LAUNCH_OK();
   count_launch();
   return 0;
 }
 
-template <int NB, bool XONLY>
-int launch_nb(const CUtensorMap& tmap, const float* mask, const GramArgs& g, int grid, double* partials, double* yside,
-              cudaStream_t s) {
+template <int NB, int T>
+int launch_nb(const CUtensorMap& tx, const CUtensorMap& ty, const float* mask, const GramArgs& g, int grid,
+              double* partials, double* xside, double* yside, cudaStream_t s) {
 #ifdef PDSB_TC_ABLATION
   // timing ablations of the bench shape only (results are garbage): PDSB_TC_DBG = 1 no TMEM store, 2 no lo arithmetic,
-  // 4 no shared-memory loads, 8 no MMA, 15 all of them
+  // 4 no shared-memory loads, 8 no MMA, 15 all of them; 16 = full kernel + timeline trace of CTA 0
   static int dbg = [] { const char* e = getenv("PDSB_TC_DBG"); return e ? atoi(e) : 0; }();
-  if (NB == 3 && !XONLY) {
+  if (NB == 2 && T == 1) {
     switch (dbg) {
-      case 1: return launch_one<NB, XONLY, 2, 1>(tmap, mask, g, grid, partials, yside, s);
-      case 2: return launch_one<NB, XONLY, 2, 2>(tmap, mask, g, grid, partials, yside, s);
-      case 4: return launch_one<NB, XONLY, 2, 4>(tmap, mask, g, grid, partials, yside, s);
-      case 8: return launch_one<NB, XONLY, 2, 8>(tmap, mask, g, grid, partials, yside, s);
-      case 7: return launch_one<NB, XONLY, 2, 7>(tmap, mask, g, grid, partials, yside, s);
-      case 15: return launch_one<NB, XONLY, 2, 15>(tmap, mask, g, grid, partials, yside, s);
-      case 16: return launch_one<NB, XONLY, 2, 16>(tmap, mask, g, grid, partials, yside, s);   // timeline trace of CTA 0
+      case 1: return launch_one<NB, T, 1>(tx, ty, mask, g, grid, partials, xside, yside, s);
+      case 2: return launch_one<NB, T, 2>(tx, ty, mask, g, grid, partials, xside, yside, s);
+      case 4: return launch_one<NB, T, 4>(tx, ty, mask, g, grid, partials, xside, yside, s);
+      case 8: return launch_one<NB, T, 8>(tx, ty, mask, g, grid, partials, xside, yside, s);
+      case 7: return launch_one<NB, T, 7>(tx, ty, mask, g, grid, partials, xside, yside, s);
+      case 15: return launch_one<NB, T, 15>(tx, ty, mask, g, grid, partials, xside, yside, s);
+      case 16: return launch_one<NB, T, 16>(tx, ty, mask, g, grid, partials, xside, yside, s);
       default: break;
     }
   }
 #endif
-  if (conv_sets() == 3) return launch_one<NB, XONLY, 3, 0>(tmap, mask, g, grid, partials, yside, s);
-  return launch_one<NB, XONLY, 2, 0>(tmap, mask, g, grid, partials, yside, s);
+  return launch_one<NB, T, 0>(tx, ty, mask, g, grid, partials, xside, yside, s);
+}
+
+// geometry of one call: where X and Y lie
+struct Geometry {
+  const float* xbase; const float* ybase;   // column-major: first feature / target column;  blocked: the frame (both)
+  int64_t ldx, ldy;
+  int ncols, xcol, ycol;                    // blocked frame
+  bool blocked;
+};
+
+int encode_maps(const Geometry& g, int64_t n, int p, int t, CUtensorMap* tx, CUtensorMap* ty) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return -1;
+  CUresult cr = CUDA_SUCCESS;
+  for (int which = 0; which < 2 && cr == CUDA_SUCCESS; ++which) {
+    CUtensorMap* tm = which ? ty : tx;
+    const int cols = which ? t : p;
+    if (g.blocked) {
+      // row-blocked frame: [block][column][128 rows] -> every 128-row x ncols stage is ONE contiguous run in HBM.
+      // (column-major matrices cap this kernel at 4.3 TB/s even with all arithmetic removed; blocked: 6.5+ TB/s)
+      cuuint64_t dims3[3] = {(cuuint64_t)STAGE_ROWS, (cuuint64_t)g.ncols, (cuuint64_t)ceil_div(n, (int64_t)STAGE_ROWS)};
+      cuuint64_t strides3[2] = {(cuuint64_t)STAGE_ROWS * sizeof(float), (cuuint64_t)STAGE_ROWS * g.ncols * sizeof(float)};
+      cuuint32_t box3[3] = {(cuuint32_t)BOX_ROWS, (cuuint32_t)cols, 1};
+      cuuint32_t estr3[3] = {1, 1, 1};
+      cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(g.xbase), dims3, strides3, box3, estr3,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      const int64_t ld = which ? g.ldy : g.ldx;
+      cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)cols};
+      cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+      cuuint32_t box[2] = {(cuuint32_t)BOX_ROWS, (cuuint32_t)cols};
+      cuuint32_t estr[2] = {1, 1};
+      cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(which ? g.ybase : g.xbase), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+  }
+  if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return 1; }
+  return 0;
+}
+
+int moments_tcgen05_core(const Geometry& geo, const float* mask, int64_t n, int p, int t, double* M, cudaStream_t s) {
+  CUtensorMap tx, ty;
+  if (int rc = encode_maps(geo, n, p, t, &tx, &ty)) return rc;
+  GramArgs a;
+  a.n = n; a.stages_total = ceil_div(n, (int64_t)STAGE_ROWS); a.p = p; a.t = t; a.xcol = geo.xcol; a.ycol = geo.ycol;
+  a.blocked = geo.blocked ? 1 : 0; a.explicit_hi = (tc_mode() == 0) ? 1 : 0;
+  const int NB = (p + 15) / 16, N = NB * 16, T = (t == 1) ? 1 : MAX_T;
+  int grid = sm_count();
+  if (a.stages_total < grid) grid = (int)a.stages_total;
+  const size_t n_part = (size_t)grid * 128 * N, n_xs = (size_t)grid * NSIDE * (T + 1) * XSIDE_COLS, n_ys = (size_t)grid * NSIDE * YSIDE_STRIDE;
+  double* partials = nullptr;
+  if (dev_alloc((void**)&partials, (n_part + n_xs + n_ys) * sizeof(double), s)) return 1;
+  double* xside = partials + n_part;
+  double* yside = xside + n_xs;
+  int rc;
+#define PDSB_GO(NBV) (t == 1 ? launch_nb<NBV, 1>(tx, ty, mask, a, grid, partials, xside, yside, s) \
+                             : launch_nb<NBV, MAX_T>(tx, ty, mask, a, grid, partials, xside, yside, s))
+  switch (NB) {
+    case 1: rc = PDSB_GO(1); break;
+    case 2: rc = PDSB_GO(2); break;
+    case 3: rc = PDSB_GO(3); break;
+    default: rc = PDSB_GO(4); break;
+  }
+#undef PDSB_GO
+  if (!rc) {
+    const int q1 = p + t + 1;
+    gram_finalize_kernel<<<(q1 * q1 + 127) / 128, 128, 0, s>>>(partials, xside, yside, grid, N, T, p, t, n, mask ? 1 : 0, M);
+    cudaError_t e = cudaGetLastError();
+    count_launch();
+    if (e != cudaSuccess) { set_error("gram finalize launch failed: %s", cudaGetErrorString(e)); rc = 1; }
+  }
+  dev_free(partials, s);
+  return rc;
 }
 
 }  // namespace
@@ -701,112 +748,37 @@ extern "C" int pdsb_debug_tc_trace(unsigned long long* host, int max_stages) {
 }
 #endif
 
+// column-major matrices: X = p columns with leading dimension ldx, Y = t columns with ldy (anywhere in memory)
 bool moments_tcgen05_supported(const float* X, int64_t ldx, const float* Y, int64_t ldy, int64_t n, int p, int t) {
   if (getenv("PDSB_DISABLE_TCGEN05")) return false;
   if (n < 4096) return false;                 // latency-bound sizes stay on the SIMT kernel
-  if (n >= (int64_t(1) << 31) - STAGE_ROWS) return false;   // the 2-D tensor map is addressed with int32 row coordinates
-  if (!get_encode_fn()) return false;
-  return analyse(X, ldx, Y, ldy, p, t).ok;
+  if (n >= (int64_t(1) << 31) - STAGE_ROWS) return false;   // the 2-D tensor maps are addressed with int32 row coordinates
+  if (!get_encode_fn() || !shape_ok(p, t)) return false;
+  if ((ldx % 4) != 0 || (ldy % 4) != 0) return false;       // global strides of a tensor map are multiples of 16 bytes
+  return ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0;
 }
-
-static int moments_tcgen05_core(const Geometry& g, int64_t ldx, const float* mask, int64_t n, int p, int t, double* M,
-                                cudaStream_t s);
 
 int moments_tcgen05_f32(const float* X, int64_t ldx, const float* Y, int64_t ldy, const float* mask, int64_t n, int p,
                         int t, double* M, cudaStream_t s) {
-  const Geometry g = analyse(X, ldx, Y, ldy, p, t);
-  if (!g.ok) return -1;
-  return moments_tcgen05_core(g, ldx, mask, n, p, t, M, s);
+  if (!moments_tcgen05_supported(X, ldx, Y, ldy, n, p, t)) return -1;
+  Geometry g{X, Y, ldx, ldy, 0, 0, 0, false};
+  return moments_tcgen05_core(g, mask, n, p, t, M, s);
 }
 
-// row-blocked frame: [block][column][FRAME_ROWS]; the frame holds exactly the p + t columns, X at xcol, Y at ycol
+// row-blocked frame: [block][column][FRAME_ROWS]; X = columns xcol .. xcol+p-1, Y = columns ycol .. ycol+t-1
 bool moments_tcgen05_frame_supported(int64_t n, int ncols, int xcol, int p, int ycol, int t) {
   if (getenv("PDSB_DISABLE_TCGEN05") || !get_encode_fn()) return false;
-  if (n < 4096 || !shape_ok(p, t) || ncols != p + t) return false;
-  if (ceil_div(n, (int64_t)STAGE_ROWS) >= (int64_t(1) << 31)) return false;     // int32 block coordinate of the 3-D tensor map
-  return (xcol == 0 && ycol == p) || (ycol == 0 && xcol == t);
+  if (n < 4096 || !shape_ok(p, t)) return false;
+  if (xcol < 0 || ycol < 0 || xcol + p > ncols || ycol + t > ncols) return false;
+  return ceil_div(n, (int64_t)STAGE_ROWS) < (int64_t(1) << 31);     // int32 block coordinate of the 3-D tensor maps
 }
 
 int moments_tcgen05_frame_f32(const float* frame, int64_t n, int ncols, int xcol, int p, int ycol, int t, const float* mask,
                               double* M, cudaStream_t s) {
   if (!moments_tcgen05_frame_supported(n, ncols, xcol, p, ycol, t)) return -1;
   if (reinterpret_cast<uintptr_t>(frame) & 15) return -1;
-  Geometry g{frame, p + t, xcol, ycol, true, true};
-  return moments_tcgen05_core(g, 0, mask, n, p, t, M, s);
-}
-
-static int moments_tcgen05_core(const Geometry& g, int64_t ldx, const float* mask, int64_t n, int p, int t, double* M,
-                                cudaStream_t s) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return -1;
-  const int q = g.q, qt = q + 1;
-  // features-only A side: chosen explicitly (mode 3) or whenever Z~ has more than 64 columns
-  const bool xonly = (tc_mode() == 3 || qt > 64) && (p + 2 * t + 1 <= 80) && t <= 4;
-  const int N = xonly ? ((p + 2 * t + 1 + 15) / 16) * 16 : ((qt + 15) / 16) * 16;
-  CUtensorMap tmap;
-  CUresult cr;
-  if (g.blocked) {
-    // row-blocked frame: [block][column][128 rows] -> every 128-row x q stage is ONE contiguous 512*q-byte run in HBM.
-    // (column-major frames cap this kernel at 4.3 TB/s even with all arithmetic removed; blocked: 6.5 TB/s)
-    cuuint64_t dims3[3] = {(cuuint64_t)STAGE_ROWS, (cuuint64_t)q, (cuuint64_t)ceil_div(n, (int64_t)STAGE_ROWS)};
-    cuuint64_t strides3[2] = {(cuuint64_t)STAGE_ROWS * sizeof(float), (cuuint64_t)STAGE_ROWS * q * sizeof(float)};
-    cuuint32_t box3[3] = {(cuuint32_t)BOX_ROWS, (cuuint32_t)q, 1};
-    cuuint32_t estr3[3] = {1, 1, 1};
-    cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(g.base), dims3, strides3, box3, estr3,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  } else {
-    cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)q};
-    cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BOX_ROWS, (cuuint32_t)q};
-    cuuint32_t estr[2] = {1, 1};
-    cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(g.base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  }
-  if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return 1; }
-  GramArgs a;
-  a.n = n; a.stages_total = ceil_div(n, (int64_t)STAGE_ROWS); a.q = q; a.p = p; a.t = t; a.zx = g.zx; a.zy = g.zy;
-  a.blocked = g.blocked ? 1 : 0; a.explicit_hi = (tc_mode() == 0) ? 1 : 0;
-  int grid = sm_count();
-  if (a.stages_total < grid) grid = (int)a.stages_total;
-  double* partials = nullptr;
-  if (dev_alloc((void**)&partials, ((size_t)grid * 128 * N + (size_t)grid * 3 * YSIDE_STRIDE) * sizeof(double), s)) return 1;
-  double* yside = partials + (size_t)grid * 128 * N;
-  int rc;
-  const int q1 = p + t + 1;
-  if (xonly) {
-    switch (N / 16) {
-      case 1: rc = launch_nb<1, true>(tmap, mask, a, grid, partials, yside, s); break;
-      case 2: rc = launch_nb<2, true>(tmap, mask, a, grid, partials, yside, s); break;
-      case 3: rc = launch_nb<3, true>(tmap, mask, a, grid, partials, yside, s); break;
-      case 4: rc = launch_nb<4, true>(tmap, mask, a, grid, partials, yside, s); break;
-      default: rc = launch_nb<5, true>(tmap, mask, a, grid, partials, yside, s); break;
-    }
-    if (!rc) {
-      gram_finalize_xonly_kernel<<<(q1 * q1 + 127) / 128, 128, 0, s>>>(partials, yside, grid, conv_sets(), N, p, t, g.zx, g.zy, n,
-                                                                    mask ? 1 : 0, M);
-      cudaError_t e = cudaGetLastError();
-      count_launch();
-      if (e != cudaSuccess) { set_error("gram finalize launch failed: %s", cudaGetErrorString(e)); rc = 1; }
-    }
-    dev_free(partials, s);
-    return rc;
-  }
-  switch (N / 16) {
-    case 1: rc = launch_nb<1, false>(tmap, mask, a, grid, partials, yside, s); break;
-    case 2: rc = launch_nb<2, false>(tmap, mask, a, grid, partials, yside, s); break;
-    case 3: rc = launch_nb<3, false>(tmap, mask, a, grid, partials, yside, s); break;
-    default: rc = launch_nb<4, false>(tmap, mask, a, grid, partials, yside, s); break;
-  }
-  if (!rc) {
-    gram_finalize_kernel<<<(q1 * q1 + 7) / 8, 256, 0, s>>>(partials, grid, N, p, t, g.zx, g.zy, M);   // 8 warps = 8 elements per block
-    cudaError_t e = cudaGetLastError();
-    count_launch();
-    if (e != cudaSuccess) { set_error("gram finalize launch failed: %s", cudaGetErrorString(e)); rc = 1; }
-  }
-  dev_free(partials, s);
-  return rc;
+  Geometry g{frame, frame, 0, 0, ncols, xcol, ycol, true};
+  return moments_tcgen05_core(g, mask, n, p, t, M, s);
 }
 
 }  // namespace pdsb

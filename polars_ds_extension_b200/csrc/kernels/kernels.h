@@ -11,11 +11,11 @@ template <typename T>
 int moments_simt(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, const T* mask, int64_t n,
                  int p, int t, double* M, cudaStream_t s, int64_t bstride = 0 /* frame block stride (elements) or 0 */);
 
-// K2b tcgen05 + TMA moments, f32, 3xTF32 split (hi/lo), f64 flush.  Returns 0 ok, 1 error,
+// K2b tcgen05 + TMA moments, f32, 3xTF32 split (hi/lo), f64 flush; p <= 64 features, t <= 4 targets.  Returns 0 ok, 1 error,
 // -1 "shape not supported by this kernel" (caller uses K2a).
 int moments_tcgen05_f32(const float* X, int64_t ldx, const float* Y, int64_t ldy, const float* mask,
                         int64_t n, int p, int t, double* M, cudaStream_t s);
-void set_tc_mode(int m);   // 0 explicit-hi, 1 raw-hi (default), 3 x-only A
+void set_tc_mode(int m);   // 1 raw hi operand (default), 0 the hi lanes clear the low 13 bits themselves (cross-check)
 constexpr int FRAME_ROWS = 128;   // rows per block of the row-blocked frame layout: [block][column][FRAME_ROWS]
 bool moments_tcgen05_frame_supported(int64_t n, int ncols, int xcol, int p, int ycol, int t);
 int moments_tcgen05_frame_f32(const float* frame, int64_t n, int ncols, int xcol, int p, int ycol, int t, const float* mask,
@@ -70,6 +70,14 @@ int gather_colmajor(const T* src, int64_t rs, int64_t cs, int64_t n, int p, T* d
 int predict_strided(const double* X, int64_t rs, int64_t cs, int64_t n, int p, const double* beta, int has_bias,
                     double* out, cudaStream_t s);
 int woodbury_update(double* inv, double* w, int q, int has_bias, const double* x, double y, double c, cudaStream_t s);
+
+// K11 logistic regression (IRLS row pass: weights, working response, summed log-loss per block; probabilities)
+int irls_max_parts();
+template <typename T>
+int irls_rows(const T* X, int64_t ldx, const T* y, const T* mask, int64_t n, int p, int add_bias, const double* beta,
+              T* w, T* z, double* loss_parts, int* n_parts, cudaStream_t s);
+template <typename T>
+int sigmoid_predict(const T* X, int64_t ldx, int64_t n, int p, int add_bias, const double* beta, T* out, cudaStream_t s);
 
 // K9 report
 template <typename T>

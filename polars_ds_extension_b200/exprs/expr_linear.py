@@ -18,7 +18,7 @@ from .. import config as cfg
 from ..frame import ColExpr, PluginExpr, col
 from ..typing import LRSolverMethods, NullPolicy
 
-__all__ = ["lin_reg", "simple_lin_reg", "query_ar_coeffs", "linear_impute", "lin_reg_w_rcond", "recursive_lin_reg", "rolling_lin_reg", "lin_reg_report"]
+__all__ = ["lin_reg", "logistic_reg", "simple_lin_reg", "query_ar_coeffs", "linear_impute", "lin_reg_w_rcond", "recursive_lin_reg", "rolling_lin_reg", "lin_reg_report"]
 
 ExprLike = Union[str, ColExpr]
 
@@ -86,6 +86,24 @@ def lin_reg(
     if return_pred:
         return PluginExpr(cfg._which_lin_reg("pl_lr_pred"), cols, kwargs, out_name="lr_pred")
     return PluginExpr(cfg._which_lin_reg("pl_lr"), cols, kwargs, returns_scalar=True, out_name="coeffs")
+
+
+def logistic_reg(*x: ExprLike, target: ExprLike, add_bias: bool = True, l1_reg: float = 0.0, l2_reg: float = 0.0,
+                 tol: float = 1e-5, max_iter: int = 200, null_policy: NullPolicy = "skip",
+                 return_pred: bool = False) -> PluginExpr:
+    """Binary logistic regression (target must be 0 / 1): coefficients (bias last) or, with `return_pred`, the predicted
+    probabilities.  Reference: expr_linear.py:277-354 -> pl_logistic_coeffs / pl_logistic_pred, always float64.  The
+    reference minimises the mean log-loss (+ l2 / 2 |w|^2, + l1 |w|_1) with L-BFGS; here the same minimiser is reached
+    by Newton / IRLS on the device (csrc/host/lr_host.cc::host_logistic)."""
+    if max_iter <= 0:
+        raise ValueError("Input `max_iter` must be a positive.")
+    kwargs = {"bias": add_bias, "null_policy": null_policy, "l1_reg": l1_reg, "l2_reg": l2_reg, "solver": "",
+              "tol": abs(tol), "max_iter": max_iter}
+    cols = [lr_formula(target).cast("f64")]
+    cols.extend(lr_formula(z) for z in x)
+    if return_pred:
+        return PluginExpr("pl_logistic_pred", cols, kwargs, out_name="__pred__")
+    return PluginExpr("pl_logistic_coeffs", cols, kwargs, returns_scalar=True, out_name="__coeffs__")
 
 
 def simple_lin_reg(x: ExprLike, target: ExprLike, add_bias: bool = False, weights: ExprLike | None = None,

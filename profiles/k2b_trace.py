@@ -44,7 +44,7 @@ def d(a, b):
 
 
 period = float(np.mean(np.diff(t[lo:hi, 6])))
-ring = {1: 6, 2: 6, 3: 6, 4: 5, 5: 4}[(p + 2 + 15) // 16]
+ring = {1: 10, 2: 10, 3: 7, 4: 5}[(p + 15) // 16]
 out = {"rows": rows, "p": p, "cycles_per_stage": round(period, 1),
        "tma_issue->conv_sees_tile (HBM latency + queueing)": d(0, 2),
        "conv_sees_tile->conv_has_A_slot": d(2, 3),

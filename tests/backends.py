@@ -69,8 +69,10 @@ class PluginBackend:
     def normalize(self, e: PluginExpr, res: pa.Array):
         f32 = e.symbol.endswith("_f32")
         base = e.symbol[:-4] if f32 else e.symbol
-        if base == "pl_lr":
+        if base in ("pl_lr", "pl_logistic_coeffs"):
             return _list_or_none(res[0])
+        if base == "pl_logistic_pred":
+            return _masked(res)
         if base == "pl_lr_pred":
             return {"pred": _masked(res.field("pred")), "resid": _masked(res.field("resid"))}
         if base == "pl_lr_multi":

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     L = lib()
     missing = [s for s in sorted(_declared_symbols()) if not hasattr(L, s)]
     assert not missing, missing
-    assert len([s for s in _declared_symbols() if s.startswith("_polars_plugin_pl_")]) == 20
+    assert len([s for s in _declared_symbols() if s.startswith("_polars_plugin_pl_")]) == 22   # 18 lin_reg symbols + pl_lr_by{,_f32} + 2 logistic
     L._polars_plugin_get_version.restype = C.c_uint32
     assert L._polars_plugin_get_version() == 1          # major 0, minor 1
     assert L.pdsb_version() == 0x000100
@@ -47,8 +47,10 @@ def test_schema_twins():
         f = _harness.field_of(sym)
         T = pa.float32() if sym.endswith("_f32") else pa.float64()
         base = sym[:-4] if sym.endswith("_f32") else sym
-        if base in ("pl_lr", "pl_lr_multi"):
+        if base in ("pl_lr", "pl_lr_multi", "pl_logistic_coeffs"):
             assert f.name == "coeffs" and f.type == pa.large_list(pa.field("item", T))
+        elif base == "pl_logistic_pred":          # #[polars_expr(output_type=Float64)], logistic_regression.rs:50
+            assert f.type == pa.float64()
         elif base in ("pl_lr_pred", "pl_lr_multi_pred"):
             assert [c.name for c in f.type] == ["pred", "resid"] and f.type.field(0).type == T
         elif base == "pl_lr_w_rcond":
