@@ -58,14 +58,14 @@ constexpr int A_COL0 = 2 * D_COLS;
 constexpr int FLUSH_STAGES = 2;         // accumulate 2 stages = 256 rows in fp32 (RZ accumulation) before draining to f64
 constexpr int NCONV = 2;                // converter warp sets, alternating stages
 constexpr int EPI_SETS = 2;             // epilogue warp sets, each draining half of the accumulator columns
-constexpr int NSIDE = 2;                  // side warps: warp k takes boxes 2k, 2k+1 of every stage (x . y, sum x, sum y, y . y, count)
-constexpr int NUM_WARPS = 2 + 4 * NCONV + NSIDE + 4 * EPI_SETS;
+constexpr int NUM_WARPS = 4 * NCONV + 4 * EPI_SETS + 4;     // warps 16, 17 idle; 18 = MMA issuer, 19 = TMA producer
 constexpr int NUM_THREADS = NUM_WARPS * 32;     // 640 (96 registers per thread)
 constexpr int TMEM_COLS = 512;
 constexpr int A_SLOT_COLS = BPS * BOX_ROWS;
 constexpr int Y_ROWS = 8;               // tile rows reserved for the targets (t <= 4; one 8-row swizzle group)
 constexpr int MAX_T = 4;
 constexpr uint32_t HI_MASK = 0xFFFFE000u;   // TF32 keeps 10 mantissa bits
+constexpr int SIDE_SLOTS = 4;             // partial slots per CTA for the side sums (4 side warps, or the 2 converter sets; zero-filled)
 constexpr int XSIDE_COLS = 64;          // doubles per (CTA, converter set, slot): slot j < T = x . y_j, slot T = sum x
 constexpr int YSIDE_STRIDE = 32;        // doubles per (CTA, converter set): [3u+0] sum y_u, [3u+1] sum y_u^2, [2] count, [12 + 4j + k] y_j.y_k
 
@@ -198,7 +198,7 @@ __host__ __device__ __forceinline__ int hi_lane(int c) { return (c >> 4) * 32 + 
 
 #ifdef PDSB_TC_ABLATION
 // timeline of CTA 0 (ablation builds): clock64 stamps, [stage][event]
-constexpr int TRACE_STAGES = 2048, TRACE_EVENTS = 12;
+constexpr int TRACE_STAGES = 2048, TRACE_EVENTS = 16;
 __device__ unsigned long long g_trace[TRACE_STAGES * TRACE_EVENTS];
 #define PDSB_TRACE(stage, ev)                                                                                   \
   do {                                                                                                          \
@@ -215,6 +215,7 @@ struct GramArgs {
   int xcol, ycol;        // row-blocked frame: first feature / target column of the frame
   int blocked;           // row-blocked frame (3-D tensor maps) or column-major matrices (2-D)
   int explicit_hi;       // cross-check: the hi lanes clear the low 13 bits themselves
+  int joined;            // Y follows X in memory and p is a multiple of 16: ONE box {32 x (p + t)} per load lands Y at tile row N
 };
 
 // T = targets the side lanes are compiled for (1, or 4 for t = 2..4).  DBG = timing ablations (never in production:
@@ -223,7 +224,7 @@ template <int NB, int T, int DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
                     const float* __restrict__ mask, const GramArgs g, double* __restrict__ partials /* [grid][128][N] */,
-                    double* __restrict__ xside /* [grid][NSIDE][T+1][64] */, double* __restrict__ yside /* [grid][NSIDE][32] */) {
+                    double* __restrict__ xside /* [grid][SIDE_SLOTS][T+1][64] */, double* __restrict__ yside /* [grid][SIDE_SLOTS][32] */  /* both zero-filled */) {
   using S = Shape<NB>;
   constexpr int N = S::N, NH = S::NH, RING = S::RING;
   constexpr uint32_t TILE_BYTES = S::TILE_BYTES;
@@ -242,7 +243,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   auto stage_row0 = [&](uint32_t it) { return ((int64_t)it * gridDim.x + blockIdx.x) * STAGE_ROWS; };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < RING; ++i) { mbar_init(&bars->raw_full[i], 1); mbar_init(&bars->raw_empty[i], 1 + NSIDE); }   // the MMA's commit + the side warps
+    for (int i = 0; i < RING; ++i) { mbar_init(&bars->raw_full[i], 1); mbar_init(&bars->raw_empty[i], NB <= 2 ? 1 + BPS : 1); }   // the MMA's commit (+ the side warps, which read the tile on their own)
     for (int i = 0; i < AB; ++i) { mbar_init(&bars->a_full[i], nact); mbar_init(&bars->a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->d_full[i], 1); mbar_init(&bars->d_empty[i], nact * EPI_SETS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -267,7 +268,39 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 0) {
+  // Roles.  A warp runs on scheduler (warp id & 3) and may only touch TMEM quadrant (warp id & 3), so converters and
+  // epilogue warps come two per residue (warps 0..15); warps 18 / 19 are the MMA issuer and the TMA producer (the MMA
+  // warp's serial loop is the kernel's critical path: it should not wait for issue slots behind converters).
+  enum { R_TMA, R_MMA, R_CONV, R_SIDE, R_EPI, R_NONE };
+  const int wr = warp & 3, wk = warp >> 2;
+  // x . y_j / sum x / y sums: up to 32 features the four converter warps of quadrants 2 and 3 hold no A lanes and take one
+  // box of every stage each (the two busy converter warps per set stay at ~57 instructions per box: with the sums inside
+  // them the p = 32 stage took 2400 instead of 650 cycles, profiles/r02).  Above 32 features every converter warp is busy
+  // and has twice the time per stage: there the sums ride on the values the converter lanes hold anyway.
+  constexpr bool SIDE_WARPS = (NB <= 2);
+  int role = R_NONE, sw_id = 0;
+  if (wk == 4) {
+    // the two serial warps sit on the schedulers of quadrants 2 / 3, which hold no A lanes up to 32 features
+    if (wr == 3) role = R_TMA;
+    else if (wr == 2) role = R_MMA;
+  } else if (wk < NCONV) {
+    if (wr < nact) role = R_CONV;
+    else if (wk == 0) {   // (side warps included: they zero their quadrant first)
+      // lanes nobody feeds: zero them once so the MMA never multiplies uninitialised TMEM (their accumulator rows are
+      // not read either way)
+      const uint32_t lane_addr = (uint32_t)(wr * 32) << 16;
+      uint32_t z[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) z[k] = 0u;
+      for (int c = 0; c < AB * BPS; ++c) tmem_st32(tmem + lane_addr + (uint32_t)(A_COL0 + c * BOX_ROWS), z);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    if (SIDE_WARPS && wr >= 2) { role = R_SIDE; sw_id = wk * 2 + (wr - 2); }
+  } else {
+    role = R_EPI;
+  }
+
+  if (role == R_TMA) {
     // =============================== TMA producer (warp-uniform loop, one elected lane issues) ===============
     uint32_t rs = 0, ph = 0;
     for (uint32_t it = 0; it < my_stages; ++it) {
@@ -281,180 +314,278 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           unsigned char* dst = raw + ((size_t)rs * BPS + b) * TILE_BYTES;
           if (g.blocked) {
             tma_load_3d(dst, &tmap_x, &bars->raw_full[rs], b * BOX_ROWS, g.xcol, (int)(row0 / STAGE_ROWS));
-            tma_load_3d(dst + N * 128, &tmap_y, &bars->raw_full[rs], b * BOX_ROWS, g.ycol, (int)(row0 / STAGE_ROWS));
+            if (!g.joined) tma_load_3d(dst + N * 128, &tmap_y, &bars->raw_full[rs], b * BOX_ROWS, g.ycol, (int)(row0 / STAGE_ROWS));
           } else {
             tma_load_2d(dst, &tmap_x, &bars->raw_full[rs], (int)(row0 + b * BOX_ROWS), 0);
-            tma_load_2d(dst + N * 128, &tmap_y, &bars->raw_full[rs], (int)(row0 + b * BOX_ROWS), 0);
+            if (!g.joined) tma_load_2d(dst + N * 128, &tmap_y, &bars->raw_full[rs], (int)(row0 + b * BOX_ROWS), 0);
           }
         }
       }
       __syncwarp();
+      PDSB_TRACE(it, 14);
       if (++rs == RING) { rs = 0; ph ^= 1; }
     }
-  } else if (warp == 1) {
+  } else if (role == R_MMA) {
     // =============================== MMA issuer (warp-uniform loop, one elected lane issues) ===============
     // instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t raw_addr = smem_u32(raw);
-    uint32_t s = 0, ph = 0, rs = 0, fl = 0, buf = 0, dph = 0;   // A slot / phase, ring slot, position in flush group, D buffer / phase
-    for (uint32_t it = 0; it < my_stages; ++it) {
-      if (fl == 0) mbar_wait(&bars->d_empty[buf], dph ^ 1);
-      PDSB_TRACE(it, 1);
-      mbar_wait(&bars->a_full[s], ph);      // converters only signal after raw_full: B (the tile) has landed too
-      PDSB_TRACE(it, 11);
-      tc_fence_after();
-      PDSB_TRACE(it, 6);
-      if (elect_one()) {
-        const uint32_t d_addr = tmem + buf * D_COLS;
-        const uint32_t a_base = tmem + A_COL0 + s * A_SLOT_COLS;
-        const uint64_t bd0 = make_b_desc(raw_addr + rs * (BPS * TILE_BYTES));
-        if (!(DBG & 8)) {
+    // One loop trip = one flush group (FLUSH_STAGES stages into one accumulator buffer), unrolled: the timeline of the
+    // per-stage loop (profiles/r02) showed ~400 of its ~800 cycles per stage outside tcgen05.mma issue — every barrier
+    // test, fence and commit of this warp queues behind the converters' shared-memory traffic — so the bookkeeping is
+    // paid once per group and the a_full test of the second stage runs while the first stage's MMAs execute.  (Testing
+    // both barriers first and issuing the group's 32 MMAs back to back measured 2 % slower: profiles/r02/k2b notes.)
+    uint32_t s = 0, ph = 0, rs = 0, buf = 0, dph = 0;   // A slot / phase, ring slot, D buffer / phase
+    for (uint32_t it0 = 0; it0 < my_stages; it0 += FLUSH_STAGES) {
+      mbar_wait(&bars->d_empty[buf], dph ^ 1);
+      PDSB_TRACE(it0, 1);
+      const uint32_t d_addr = tmem + buf * D_COLS;
 #pragma unroll
-          for (int b = 0; b < BPS; ++b) {
+      for (int fl = 0; fl < FLUSH_STAGES; ++fl) {
+        const uint32_t it = it0 + fl;
+        if (it < my_stages) {                 // warp-uniform
+          mbar_wait(&bars->a_full[s], ph);    // converters only signal after raw_full: B (the tile) has landed too
+          PDSB_TRACE(it, 11);
+          tc_fence_after();
+          PDSB_TRACE(it, 6);
+          if (elect_one()) {
+            const uint32_t a_base = tmem + A_COL0 + s * A_SLOT_COLS;
+            const uint64_t bd0 = make_b_desc(raw_addr + rs * (BPS * TILE_BYTES));
+            if (!(DBG & 8)) {
 #pragma unroll
-            for (int k = 0; k < BOX_ROWS / 8; ++k) {
-              // descriptor start address advances in 16-byte units: +TILE_BYTES per box, +32 bytes per K = 8 step
-              const uint64_t bd = bd0 + (uint64_t)((b * TILE_BYTES + k * 32) >> 4);
-              tc_mma_tf32_ts(d_addr, a_base + b * BOX_ROWS + k * 8, bd, idesc, (fl == 0 && b == 0 && k == 0) ? 0u : 1u);
+              for (int b = 0; b < BPS; ++b) {
+#pragma unroll
+                for (int k = 0; k < BOX_ROWS / 8; ++k) {
+                  // descriptor start address advances in 16-byte units: +TILE_BYTES per box, +32 bytes per K = 8 step
+                  const uint64_t bd = bd0 + (uint64_t)((b * TILE_BYTES + k * 32) >> 4);
+                  tc_mma_tf32_ts(d_addr, a_base + b * BOX_ROWS + k * 8, bd, idesc, (fl == 0 && b == 0 && k == 0) ? 0u : 1u);
+                }
+              }
             }
+            tc_commit(&bars->a_empty[s]);       // TMEM A slot reusable
+            tc_commit(&bars->raw_empty[rs]);    // tile (B operand) reusable
+            if (fl == FLUSH_STAGES - 1 || it == my_stages - 1) tc_commit(&bars->d_full[buf]);
           }
+          __syncwarp();
+          PDSB_TRACE(it, 7);
+          if (++s == AB) { s = 0; ph ^= 1; }
+          if (++rs == RING) rs = 0;
         }
-        tc_commit(&bars->a_empty[s]);       // TMEM A slot reusable
-        tc_commit(&bars->raw_empty[rs]);    // tile (B operand) reusable once the side lanes have arrived too
-        if (fl == FLUSH_STAGES - 1 || it == my_stages - 1) tc_commit(&bars->d_full[buf]);
       }
-      __syncwarp();
-      PDSB_TRACE(it, 7);
-      if (++s == AB) { s = 0; ph ^= 1; }
-      if (++rs == RING) rs = 0;
-      if (++fl == FLUSH_STAGES) { fl = 0; if (buf) dph ^= 1; buf ^= 1; }
+      if (buf) dph ^= 1;
+      buf ^= 1;
     }
-  } else if (warp < 2 + 4 * NCONV) {
+  } else if (role == R_CONV) {
     // =============================== converters: NCONV sets x 4 quadrant warps; set j owns stages it = j (mod NCONV) ===
-    // tile row -> registers -> hi / lo -> tcgen05.st, nothing else: the stage rate of the kernel is set by its slowest warp
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
-    const uint32_t set = (uint32_t)(warp - 2) >> 2;
+    // Per 32-row box a lane loads the 32 rows of its feature column (8 x LDS.128), then
+    //   * adds x . y_j and sum x of those rows to packed f32 accumulators: the registers are NATURAL pairs (rows 2k, 2k+1),
+    //     the target arrives by broadcast loads in the same pairs, so this is one FFMA2 + one FADD2 per two rows and no
+    //     second pass over the tile (a separate side warp re-reading x cost 160 shared-memory wavefronts per stage and
+    //     ran at 1000 cycles per stage, profiles/r02);  lanes 16..31 hold the same x as lanes 0..15 and repeat the sums,
+    //     which costs nothing extra per warp instruction;
+    //   * turns the values into hi / lo and stores them to TMEM.
+    // The quadrant-0 warp also keeps sum y, y_j . y_k and the masked row count (8 lanes per target).
+    const int quad = wr;                       // TMEM lane quadrant this warp may touch
+    const uint32_t set = (uint32_t)wk;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    if (quad >= nact) {
-      // lanes nobody feeds: zero them once so the MMA never multiplies uninitialised TMEM (their accumulator rows are
-      // not read either way)
-      if (set == 0) {
-        uint32_t z[32];
+    const int m = quad * 16 + (lane & 15);     // feature column of this lane (lanes L and L + 16 share it)
+    // padding lanes feed accumulator rows nobody reads: they load the same address as a real lane (a broadcast)
+    const int trow = m < p ? m : 0;
+    const uint32_t sw = (uint32_t)(trow & 7);
+    // hi lanes keep the raw value (x - 0), lo lanes hold x - (x & HI_MASK): one LOP3 per element, one FADD2 per two
+    // (cross-check build: the hi lanes subtract their own low 13 bits, i.e. hold trunc(x) explicitly)
+    const uint32_t sub_mask = (lane & 16) ? HI_MASK : (g.explicit_hi ? ~HI_MASK : 0u);
+    // f32 partial sums live for SIDE_FLUSH of this warp's stages (chains of at most 64 terms, round-to-nearest) before
+    // they are added to the f64 totals: an FP64 instruction costs a warp 20-30 cycles here
+    constexpr uint32_t SIDE_FLUSH = 4;
+    float2 axy[T][2], asx[2];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) z[k] = 0u;
-        for (int c = 0; c < AB * BPS; ++c) tmem_st32(tmem + lane_addr + (uint32_t)(A_COL0 + c * BOX_ROWS), z);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      }
-    } else {
-      const int m = quad * 16 + (lane & 15);     // feature column of this lane (lanes L and L + 16 share it)
-      // padding lanes feed accumulator rows nobody reads: they load the same address as a real lane (a broadcast)
-      const int trow = m < p ? m : 0;
-      const uint32_t sw = (uint32_t)(trow & 7);
-      // hi lanes keep the raw value (x - 0), lo lanes hold x - (x & HI_MASK): one LOP3 per element, one FADD2 per two
-      // (cross-check build: the hi lanes subtract their own low 13 bits, i.e. hold trunc(x) explicitly)
-      const uint32_t sub_mask = (lane & 16) ? HI_MASK : (g.explicit_hi ? ~HI_MASK : 0u);
-      for (uint32_t it = set; it < my_stages; it += NCONV) {
-        const uint32_t rs = it % RING, rph = (it / RING) & 1;
-        const uint32_t s = it % AB, sph = (it / AB) & 1;
-        mbar_wait(&bars->raw_full[rs], rph);
-        if (quad == 0) PDSB_TRACE(it, 2);
-        mbar_wait(&bars->a_empty[s], sph ^ 1);
-        tc_fence_after();
-        if (quad == 0) PDSB_TRACE(it, 3);
+    for (int j = 0; j < T; ++j) axy[j][0] = axy[j][1] = make_float2(0.0f, 0.0f);
+    asx[0] = asx[1] = make_float2(0.0f, 0.0f);
+    double dxs[T + 1];                                          // f64: x . y_j (j < T), sum x
 #pragma unroll
-        for (int b = 0; b < BPS; ++b) {
-          uint32_t v[32];
-          const unsigned char* rowp = raw + ((size_t)rs * BPS + b) * TILE_BYTES + (size_t)trow * 128;
+    for (int j = 0; j <= T; ++j) dxs[j] = 0.0;
+    float sy = 0.0f, syy = 0.0f, sxy[3] = {0.0f, 0.0f, 0.0f};   // quadrant 0, lanes 8j + c: chunk c of target j; sxy[d-1] = y_j . y_{j+d}
+    double dsy = 0.0, dsyy = 0.0, dcnt = 0.0, dxy[3] = {0.0, 0.0, 0.0};
+    uint32_t nst = 0;
+    for (uint32_t it = set; it < my_stages; it += NCONV, ++nst) {
+      const uint32_t rs = it % RING, rph = (it / RING) & 1;
+      const uint32_t s = it % AB, sph = (it / AB) & 1;
+      mbar_wait(&bars->raw_full[rs], rph);
+      if (quad == 0) PDSB_TRACE(it, 2);
+      mbar_wait(&bars->a_empty[s], sph ^ 1);
+      tc_fence_after();
+      if (quad == 0) PDSB_TRACE(it, 3);
+#pragma unroll
+      for (int b = 0; b < BPS; ++b) {
+        const unsigned char* tile = raw + ((size_t)rs * BPS + b) * TILE_BYTES;
+        uint32_t v[32];
+        const unsigned char* rowp = tile + (size_t)trow * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 x = make_uint4(c, c + 1, c + 2, c + 3);
+          if (!(DBG & 4)) x = *reinterpret_cast<const uint4*>(rowp + ((c ^ sw) << 4));
+          v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+        }
+        if constexpr (!SIDE_WARPS) {
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+          uint4 yv[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) yv[c] = *reinterpret_cast<const uint4*>(tile + (size_t)(N + j) * 128 + ((c ^ j) << 4));   // same address in every lane
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            uint4 x = make_uint4(c, c + 1, c + 2, c + 3);
-            if (!(DBG & 4)) x = *reinterpret_cast<const uint4*>(rowp + ((c ^ sw) << 4));
-            v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+            axy[j][0] = __ffma2_rn(make_float2(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1])),
+                                   make_float2(__uint_as_float(yv[c].x), __uint_as_float(yv[c].y)), axy[j][0]);
+            axy[j][1] = __ffma2_rn(make_float2(__uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3])),
+                                   make_float2(__uint_as_float(yv[c].z), __uint_as_float(yv[c].w)), axy[j][1]);
           }
-          if (!(DBG & 2)) {
+        }
 #pragma unroll
-            for (int k = 0; k < 32; k += 2) {
-              // -(x & mask) as one LOP3: (x & mask) ^ sign   (hi lanes: x + (-0) = x; lo lanes: exact in fp32)
-              const float2 r = __fadd2_rn(make_float2(__uint_as_float(v[k]), __uint_as_float(v[k + 1])),
-                                          make_float2(__uint_as_float((v[k] & sub_mask) ^ 0x80000000u),
-                                                      __uint_as_float((v[k + 1] & sub_mask) ^ 0x80000000u)));
-              v[k] = __float_as_uint(r.x); v[k + 1] = __float_as_uint(r.y);
+        for (int c = 0; c < 8; ++c) {
+          asx[0] = __fadd2_rn(asx[0], make_float2(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1])));
+          asx[1] = __fadd2_rn(asx[1], make_float2(__uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3])));
+        }
+        }
+        if (!(DBG & 2)) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            // -(x & mask) as one LOP3: (x & mask) ^ sign   (hi lanes: x + (-0) = x; lo lanes: exact in fp32)
+            const float2 r = __fadd2_rn(make_float2(__uint_as_float(v[k]), __uint_as_float(v[k + 1])),
+                                        make_float2(__uint_as_float((v[k] & sub_mask) ^ 0x80000000u),
+                                                    __uint_as_float((v[k + 1] & sub_mask) ^ 0x80000000u)));
+            v[k] = __float_as_uint(r.x); v[k + 1] = __float_as_uint(r.y);
+          }
+        }
+        if (!(DBG & 1)) tmem_st32(tmem + lane_addr + (uint32_t)(A_COL0 + s * A_SLOT_COLS + b * BOX_ROWS), v);
+        else if (v[0] == 0x7fc12345u && v[31] == 0x12345u) bars->tmem_base = v[5];   // ablation build: keep v alive
+        if (!SIDE_WARPS && quad == 0) {               // warp-uniform
+          if (lane < 8 * t) {
+            const int j = lane >> 3, c = lane & 7;
+            const uint4 yv = *reinterpret_cast<const uint4*>(tile + (size_t)(N + j) * 128 + ((c ^ j) << 4));
+            const float y0 = __uint_as_float(yv.x), y1 = __uint_as_float(yv.y), y2 = __uint_as_float(yv.z), y3 = __uint_as_float(yv.w);
+            sy += (y0 + y1) + (y2 + y3);
+            syy = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, syy))));
+            if (T > 1) {
+#pragma unroll
+              for (int d = 1; d < 4; ++d)
+                if (j + d < t) {
+                  const int kr = j + d;
+                  const uint4 kv = *reinterpret_cast<const uint4*>(tile + (size_t)(N + kr) * 128 + ((c ^ kr) << 4));
+                  sxy[d - 1] = fmaf(y0, __uint_as_float(kv.x), fmaf(y1, __uint_as_float(kv.y),
+                               fmaf(y2, __uint_as_float(kv.z), fmaf(y3, __uint_as_float(kv.w), sxy[d - 1]))));
+                }
             }
           }
-          if (!(DBG & 1)) tmem_st32(tmem + lane_addr + (uint32_t)(A_COL0 + s * A_SLOT_COLS + b * BOX_ROWS), v);
-          else if (v[0] == 0x7fc12345u && v[31] == 0x12345u) bars->tmem_base = v[5];   // ablation build: keep v alive
+          if (mask != nullptr && lane < 8) {
+            // row count of a masked frame: the packer zeroes masked rows, so only the count needs the mask
+            const int64_t r0 = stage_row0(it) + b * BOX_ROWS + lane * 4;
+            float o = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (r0 + e < g.n) o += __ldg(mask + r0 + e);
+            dcnt += (double)o;
+          }
         }
-        if (quad == 0) PDSB_TRACE(it, 4);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->a_full[s]);
-        if (quad == 0) PDSB_TRACE(it, 5);
+      }
+      if (quad == 0) PDSB_TRACE(it, 4);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->a_full[s]);
+      if (quad == 0) PDSB_TRACE(it, 5);
+      if (!SIDE_WARPS && ((nst % SIDE_FLUSH) == SIDE_FLUSH - 1 || it + NCONV >= my_stages)) {
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+          const float2 a = __fadd2_rn(axy[j][0], axy[j][1]);
+          dxs[j] += (double)(a.x + a.y);
+          axy[j][0] = axy[j][1] = make_float2(0.0f, 0.0f);
+        }
+        const float2 a = __fadd2_rn(asx[0], asx[1]);
+        dxs[T] += (double)(a.x + a.y);
+        asx[0] = asx[1] = make_float2(0.0f, 0.0f);
+        if (quad == 0) {
+          dsy += (double)sy; dsyy += (double)syy; sy = 0.0f; syy = 0.0f;
+          if (T > 1) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { dxy[d] += (double)sxy[d]; sxy[d] = 0.0f; }
+          }
+        }
       }
     }
-  } else if (warp < 2 + 4 * NCONV + NSIDE) {
-    // =============================== side warps: warp k takes boxes 2k, 2k+1 of EVERY stage =======================
-    // lane = feature (two per lane when p > 32):  x . y_j and sum x in packed f32 (four independent chains per slot, one
-    // f64 flush per stage);  lanes 8j .. 8j+7 also hold the c-th 16-byte chunk of target j: sum y, y_j . y_k;  lanes 0..7
-    // count the rows of a masked frame.  All of it reads the tile only, so the warp releases the tile itself.
-    constexpr int NF = (NB >= 3) ? 2 : 1;      // features per lane
-    const int sw_id = warp - (2 + 4 * NCONV);
-    int frow[NF];
-    uint32_t fsw[NF];
+    if (!SIDE_WARPS && lane < 16 && m < p) {
+      double* xs = xside + ((size_t)blockIdx.x * SIDE_SLOTS + set) * (T + 1) * XSIDE_COLS;
 #pragma unroll
-    for (int f = 0; f < NF; ++f) { const int m = lane + 32 * f; frow[f] = m < p ? m : 0; fsw[f] = (uint32_t)(frow[f] & 7); }
-    double dxs[NF][T + 1];                                        // f64: x . y_j (j < T), sum x
+      for (int j = 0; j <= T; ++j) xs[j * XSIDE_COLS + m] = dxs[j];
+    }
+    if (!SIDE_WARPS && quad == 0) {
+      // reduce the 8 chunk-lanes of every target (fixed order -> reproducible) and the masked-row count
+      double* ys = yside + ((size_t)blockIdx.x * SIDE_SLOTS + set) * YSIDE_STRIDE;
+      for (int off = 4; off; off >>= 1) {
+        dsy += __shfl_down_sync(0xffffffffu, dsy, off, 8);
+        dsyy += __shfl_down_sync(0xffffffffu, dsyy, off, 8);
+        dcnt += __shfl_down_sync(0xffffffffu, dcnt, off, 8);
 #pragma unroll
-    for (int f = 0; f < NF; ++f)
+        for (int d = 0; d < 3; ++d) dxy[d] += __shfl_down_sync(0xffffffffu, dxy[d], off, 8);
+      }
+      if ((lane & 7) == 0 && (lane >> 3) < t) {
+        const int j = lane >> 3;
+        ys[j * 3 + 0] = dsy; ys[j * 3 + 1] = dsyy;
+        for (int d = 1; d < 4; ++d) if (j + d < t) ys[12 + j * 4 + (j + d)] = dxy[d - 1];
+      }
+      if (lane == 0) ys[2] = dcnt;
+    }
+  } else if (role == R_SIDE) {
+    // =============================== side warps (p <= 32): warp k takes box k of EVERY stage, lane = feature ==========
+    // x . y_j and sum x over NATURAL register pairs (a 16-byte load gives rows (4c, 4c+1), (4c+2, 4c+3) of the column, the
+    // broadcast load of y_j the same rows of the target: one FFMA2 / FADD2 per two rows); lanes 8j + c also hold chunk c of
+    // target j (sum y, y_j . y_k); lanes 0..7 count the rows of a masked frame.  All loads of the box are issued before the
+    // first FMA; f32 partial sums (chains of at most 64 terms) go to the f64 totals every SIDE_FLUSH stages.
+    if constexpr (SIDE_WARPS) {
+    constexpr uint32_t SIDE_FLUSH = 4;
+    const int b = sw_id;
+    const int frow = lane < p ? lane : 0;
+    const uint32_t fsw = (uint32_t)(frow & 7);
+    float2 axy[T][2], asx[2];
 #pragma unroll
-      for (int j = 0; j <= T; ++j) dxs[f][j] = 0.0;
+    for (int j = 0; j < T; ++j) axy[j][0] = axy[j][1] = make_float2(0.0f, 0.0f);
+    asx[0] = asx[1] = make_float2(0.0f, 0.0f);
+    double dxs[T + 1];
+#pragma unroll
+    for (int j = 0; j <= T; ++j) dxs[j] = 0.0;
+    float sy = 0.0f, syy = 0.0f, sxy[3] = {0.0f, 0.0f, 0.0f};
     double dsy = 0.0, dsyy = 0.0, dcnt = 0.0, dxy[3] = {0.0, 0.0, 0.0};
     uint32_t rs = 0, rph = 0;
     for (uint32_t it = 0; it < my_stages; ++it) {
+      if (sw_id == 0) PDSB_TRACE(it, 15);
       mbar_wait(&bars->raw_full[rs], rph);
-      // packed f32 over NATURAL register pairs: a 16-byte load gives rows (4c, 4c+1) and (4c+2, 4c+3) of a column, the
-      // broadcast load of y_j the same rows of the target -> x . y and sum x cost one FFMA2 / FADD2 per two rows, no moves.
-      // Two independent chains per sum (the two pairs of a chunk); one f64 flush per stage (64-term f32 sums, RN).
-      float2 axy[NF][T][2], asx[NF][2];
-      float sy = 0.0f, syy = 0.0f, sxy[3] = {0.0f, 0.0f, 0.0f};   // lanes 8j + c: chunk c of target j; sxy[d-1] = y_j . y_{j+d}
+      if (sw_id == 0) PDSB_TRACE(it, 12);
+      const unsigned char* tile = raw + ((size_t)rs * BPS + b) * TILE_BYTES;
+      uint4 xv[8];
 #pragma unroll
-      for (int f = 0; f < NF; ++f) {
+      for (int c = 0; c < 8; ++c) xv[c] = *reinterpret_cast<const uint4*>(tile + (size_t)frow * 128 + ((c ^ fsw) << 4));
 #pragma unroll
-        for (int j = 0; j < T; ++j) axy[f][j][0] = axy[f][j][1] = make_float2(0.0f, 0.0f);
-        asx[f][0] = asx[f][1] = make_float2(0.0f, 0.0f);
+      for (int j = 0; j < T; ++j) {
+        uint4 yv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) yv[c] = *reinterpret_cast<const uint4*>(tile + (size_t)(N + j) * 128 + ((c ^ j) << 4));   // same address in every lane
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          axy[j][0] = __ffma2_rn(make_float2(__uint_as_float(xv[c].x), __uint_as_float(xv[c].y)),
+                                 make_float2(__uint_as_float(yv[c].x), __uint_as_float(yv[c].y)), axy[j][0]);
+          axy[j][1] = __ffma2_rn(make_float2(__uint_as_float(xv[c].z), __uint_as_float(xv[c].w)),
+                                 make_float2(__uint_as_float(yv[c].z), __uint_as_float(yv[c].w)), axy[j][1]);
+        }
       }
 #pragma unroll
-      for (int bb = 0; bb < BPS / NSIDE; ++bb) {
-      const int b = sw_id * (BPS / NSIDE) + bb;
-      const unsigned char* tile = raw + ((size_t)rs * BPS + b) * TILE_BYTES;
-#pragma unroll
       for (int c = 0; c < 8; ++c) {
-        float2 y01[T], y23[T];
-#pragma unroll
-        for (int j = 0; j < T; ++j) {
-          const uint4 yv = *reinterpret_cast<const uint4*>(tile + (size_t)(N + j) * 128 + ((c ^ j) << 4));   // same address in every lane
-          y01[j] = make_float2(__uint_as_float(yv.x), __uint_as_float(yv.y));
-          y23[j] = make_float2(__uint_as_float(yv.z), __uint_as_float(yv.w));
-        }
-#pragma unroll
-        for (int f = 0; f < NF; ++f) {
-          const uint4 xv = *reinterpret_cast<const uint4*>(tile + (size_t)frow[f] * 128 + ((c ^ fsw[f]) << 4));
-          const float2 x01 = make_float2(__uint_as_float(xv.x), __uint_as_float(xv.y));
-          const float2 x23 = make_float2(__uint_as_float(xv.z), __uint_as_float(xv.w));
-#pragma unroll
-          for (int j = 0; j < T; ++j) {
-            axy[f][j][0] = __ffma2_rn(x01, y01[j], axy[f][j][0]);
-            axy[f][j][1] = __ffma2_rn(x23, y23[j], axy[f][j][1]);
-          }
-          asx[f][0] = __fadd2_rn(asx[f][0], x01);
-          asx[f][1] = __fadd2_rn(asx[f][1], x23);
-        }
+        asx[0] = __fadd2_rn(asx[0], make_float2(__uint_as_float(xv[c].x), __uint_as_float(xv[c].y)));
+        asx[1] = __fadd2_rn(asx[1], make_float2(__uint_as_float(xv[c].z), __uint_as_float(xv[c].w)));
       }
       if (lane < 8 * t) {
         const int j = lane >> 3, c = lane & 7;
         const uint4 yv = *reinterpret_cast<const uint4*>(tile + (size_t)(N + j) * 128 + ((c ^ j) << 4));
         const float y0 = __uint_as_float(yv.x), y1 = __uint_as_float(yv.y), y2 = __uint_as_float(yv.z), y3 = __uint_as_float(yv.w);
-        sy += (y0 + y1) + (y2 + y3);                                   // 8 values per lane and stage in f32, then f64
+        sy += (y0 + y1) + (y2 + y3);
         syy = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, syy))));
         if (T > 1) {
 #pragma unroll
@@ -475,52 +606,51 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         for (int e = 0; e < 4; ++e) if (r0 + e < g.n) o += __ldg(mask + r0 + e);
         dcnt += (double)o;
       }
-      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->raw_empty[rs]);           // the MMA's commit is the other arrival
+      if (sw_id == 0) PDSB_TRACE(it, 13);
+      if ((it % SIDE_FLUSH) == SIDE_FLUSH - 1 || it == my_stages - 1) {
 #pragma unroll
-      for (int f = 0; f < NF; ++f) {
+        for (int j = 0; j < T; ++j) {
+          const float2 a = __fadd2_rn(axy[j][0], axy[j][1]);
+          dxs[j] += (double)(a.x + a.y);
+          axy[j][0] = axy[j][1] = make_float2(0.0f, 0.0f);
+        }
+        const float2 a = __fadd2_rn(asx[0], asx[1]);
+        dxs[T] += (double)(a.x + a.y);
+        asx[0] = asx[1] = make_float2(0.0f, 0.0f);
+        dsy += (double)sy; dsyy += (double)syy; sy = 0.0f; syy = 0.0f;
+        if (T > 1) {
 #pragma unroll
-        for (int j = 0; j < T; ++j) { const float2 a = __fadd2_rn(axy[f][j][0], axy[f][j][1]); dxs[f][j] += (double)(a.x + a.y); }
-        const float2 a = __fadd2_rn(asx[f][0], asx[f][1]);
-        dxs[f][T] += (double)(a.x + a.y);
-      }
-      dsy += (double)sy; dsyy += (double)syy;
-      if (T > 1) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) dxy[d] += (double)sxy[d];
+          for (int d = 0; d < 3; ++d) { dxy[d] += (double)sxy[d]; sxy[d] = 0.0f; }
+        }
       }
       if (++rs == RING) { rs = 0; rph ^= 1; }
     }
-    {
-      double* xs = xside + ((size_t)blockIdx.x * NSIDE + sw_id) * (T + 1) * XSIDE_COLS;
+    if (lane < p) {
+      double* xs = xside + ((size_t)blockIdx.x * SIDE_SLOTS + sw_id) * (T + 1) * XSIDE_COLS;
 #pragma unroll
-      for (int f = 0; f < NF; ++f) {
-        const int m = lane + 32 * f;
-        if (m < p)
-#pragma unroll
-          for (int j = 0; j <= T; ++j) xs[j * XSIDE_COLS + m] = dxs[f][j];
-      }
-      // reduce the 8 chunk-lanes of every target (fixed order -> reproducible) and the masked-row count
-      double* ys = yside + ((size_t)blockIdx.x * NSIDE + sw_id) * YSIDE_STRIDE;
-      for (int off = 4; off; off >>= 1) {
-        dsy += __shfl_down_sync(0xffffffffu, dsy, off, 8);
-        dsyy += __shfl_down_sync(0xffffffffu, dsyy, off, 8);
-        dcnt += __shfl_down_sync(0xffffffffu, dcnt, off, 8);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) dxy[d] += __shfl_down_sync(0xffffffffu, dxy[d], off, 8);
-      }
-      if ((lane & 7) == 0 && (lane >> 3) < t) {
-        const int j = lane >> 3;
-        ys[j * 3 + 0] = dsy; ys[j * 3 + 1] = dsyy;
-        for (int d = 1; d < 4; ++d) if (j + d < t) ys[12 + j * 4 + (j + d)] = dxy[d - 1];
-      }
-      if (lane == 0) ys[2] = dcnt;
+      for (int j = 0; j <= T; ++j) xs[j * XSIDE_COLS + lane] = dxs[j];
     }
-  } else {
+    double* ys = yside + ((size_t)blockIdx.x * SIDE_SLOTS + sw_id) * YSIDE_STRIDE;
+    for (int off = 4; off; off >>= 1) {
+      dsy += __shfl_down_sync(0xffffffffu, dsy, off, 8);
+      dsyy += __shfl_down_sync(0xffffffffu, dsyy, off, 8);
+      dcnt += __shfl_down_sync(0xffffffffu, dcnt, off, 8);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) dxy[d] += __shfl_down_sync(0xffffffffu, dxy[d], off, 8);
+    }
+    if ((lane & 7) == 0 && (lane >> 3) < t) {
+      const int j = lane >> 3;
+      ys[j * 3 + 0] = dsy; ys[j * 3 + 1] = dsyy;
+      for (int d = 1; d < 4; ++d) if (j + d < t) ys[12 + j * 4 + (j + d)] = dxy[d - 1];
+    }
+    if (lane == 0) ys[2] = dcnt;
+    }
+  } else if (role == R_EPI) {
     // =============================== epilogue: EPI_SETS x 4 warps, set e drains columns [e*NH, (e+1)*NH) =========
-    const int quad = warp & 3;
-    const int eset = (warp - (2 + 4 * NCONV + NSIDE)) >> 2;
+    const int quad = wr;
+    const int eset = wk - NCONV;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     if (quad < nact) {
       double acc[NH];
@@ -578,12 +708,12 @@ __global__ void gram_finalize_kernel(const double* __restrict__ partials, const 
   } else if (i < p) {                              // X'y_k (slot k) and the column sums (slot T) from the converter lanes
     const int slot = (j < p + t) ? j - p : T;
     r = 0.0;
-    for (int k = 0; k < nparts * NSIDE; ++k) r += xside[((size_t)k * (T + 1) + slot) * XSIDE_COLS + i];
+    for (int k = 0; k < nparts * SIDE_SLOTS; ++k) r += xside[((size_t)k * (T + 1) + slot) * XSIDE_COLS + i];
   } else {
     // y / ones block from the side lanes
     double sy[MAX_T] = {0, 0, 0, 0}, syy[MAX_T] = {0, 0, 0, 0}, cnt = 0.0, cross = 0.0;
     const bool want_cross = (j < p + t) && (i != j);
-    for (int k = 0; k < nparts * NSIDE; ++k) {
+    for (int k = 0; k < nparts * SIDE_SLOTS; ++k) {
       const double* ys = yside + (size_t)k * YSIDE_STRIDE;
       for (int u = 0; u < t; ++u) { sy[u] += ys[u * 3 + 0]; syy[u] += ys[u * 3 + 1]; }
       cnt += ys[2];
@@ -670,13 +800,13 @@ struct Geometry {
   bool blocked;
 };
 
-int encode_maps(const Geometry& g, int64_t n, int p, int t, CUtensorMap* tx, CUtensorMap* ty) {
+int encode_maps(const Geometry& g, int64_t n, int p, int t, bool joined, CUtensorMap* tx, CUtensorMap* ty) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return -1;
   CUresult cr = CUDA_SUCCESS;
   for (int which = 0; which < 2 && cr == CUDA_SUCCESS; ++which) {
     CUtensorMap* tm = which ? ty : tx;
-    const int cols = which ? t : p;
+    const int cols = which ? t : (joined ? p + t : p);
     if (g.blocked) {
       // row-blocked frame: [block][column][128 rows] -> every 128-row x ncols stage is ONE contiguous run in HBM.
       // (column-major matrices cap this kernel at 4.3 TB/s even with all arithmetic removed; blocked: 6.5+ TB/s)
@@ -689,7 +819,7 @@ int encode_maps(const Geometry& g, int64_t n, int p, int t, CUtensorMap* tx, CUt
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
       const int64_t ld = which ? g.ldy : g.ldx;
-      cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)cols};
+      cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)cols};      // joined: X's map also spans the t target columns behind it
       cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
       cuuint32_t box[2] = {(cuuint32_t)BOX_ROWS, (cuuint32_t)cols};
       cuuint32_t estr[2] = {1, 1};
@@ -703,19 +833,24 @@ int encode_maps(const Geometry& g, int64_t n, int p, int t, CUtensorMap* tx, CUt
 }
 
 int moments_tcgen05_core(const Geometry& geo, const float* mask, int64_t n, int p, int t, double* M, cudaStream_t s) {
+  // Y right behind X and N == p: one box per load carries both (half the TMA requests; the 128-byte target boxes are as
+  // expensive to issue as the feature boxes)
+  const bool joined = (p % 16 == 0) && (geo.blocked ? geo.ycol == geo.xcol + p
+                                                     : (geo.ybase == geo.xbase + (size_t)p * geo.ldx && geo.ldx == geo.ldy));
   CUtensorMap tx, ty;
-  if (int rc = encode_maps(geo, n, p, t, &tx, &ty)) return rc;
+  if (int rc = encode_maps(geo, n, p, t, joined, &tx, &ty)) return rc;
   GramArgs a;
   a.n = n; a.stages_total = ceil_div(n, (int64_t)STAGE_ROWS); a.p = p; a.t = t; a.xcol = geo.xcol; a.ycol = geo.ycol;
-  a.blocked = geo.blocked ? 1 : 0; a.explicit_hi = (tc_mode() == 0) ? 1 : 0;
+  a.blocked = geo.blocked ? 1 : 0; a.explicit_hi = (tc_mode() == 0) ? 1 : 0; a.joined = joined ? 1 : 0;
   const int NB = (p + 15) / 16, N = NB * 16, T = (t == 1) ? 1 : MAX_T;
   int grid = sm_count();
   if (a.stages_total < grid) grid = (int)a.stages_total;
-  const size_t n_part = (size_t)grid * 128 * N, n_xs = (size_t)grid * NSIDE * (T + 1) * XSIDE_COLS, n_ys = (size_t)grid * NSIDE * YSIDE_STRIDE;
+  const size_t n_part = (size_t)grid * 128 * N, n_xs = (size_t)grid * SIDE_SLOTS * (T + 1) * XSIDE_COLS, n_ys = (size_t)grid * SIDE_SLOTS * YSIDE_STRIDE;
   double* partials = nullptr;
   if (dev_alloc((void**)&partials, (n_part + n_xs + n_ys) * sizeof(double), s)) return 1;
   double* xside = partials + n_part;
   double* yside = xside + n_xs;
+  PDSB_CUDA_OK(cudaMemsetAsync(xside, 0, (n_xs + n_ys) * sizeof(double), s));     // not every slot has a writer
   int rc;
 #define PDSB_GO(NBV) (t == 1 ? launch_nb<NBV, 1>(tx, ty, mask, a, grid, partials, xside, yside, s) \
                              : launch_nb<NBV, MAX_T>(tx, ty, mask, a, grid, partials, xside, yside, s))

@@ -28,12 +28,12 @@ for _ in range(3):
     dev.moments_frame(frame, rows, p + 1, 0, p, p, 1, out=M)
 torch.cuda.synchronize()
 NS = 2048
-buf = np.zeros((NS, 12), dtype=np.uint64)
+buf = np.zeros((NS, 16), dtype=np.uint64)
 L = lib()
 L.pdsb_debug_tc_trace.argtypes = [C.c_void_p, C.c_int]
 L.pdsb_debug_tc_trace.restype = C.c_int
 ne = L.pdsb_debug_tc_trace(buf.ctypes.data, NS)
-assert ne == 12, ne
+assert ne == 16, ne
 t = buf.astype(np.int64)
 lo, hi = 200, 1800          # steady state
 
@@ -57,6 +57,11 @@ out = {"rows": rows, "p": p, "cycles_per_stage": round(period, 1),
        "slot hold: tma issue(it) -> slot free (it+RING)": round(float(np.mean(t[lo + ring:hi + ring, 0] - t[lo:hi, 0])), 1),
        "producer stall: slot free(it) - slot free(it-1)": round(float(np.mean(np.diff(t[lo:hi, 0]))), 1),
        }
+out["side warp 0: loop top -> tile seen"] = d(15, 12)
+out["side warp 0: work (2 boxes) + arrive"] = d(12, 13)
+out["side warp 0: period"] = round(float(np.mean(np.diff(t[lo:hi, 12]))), 1)
+out["side warp 0 lag behind the converter (tile seen)"] = d(2, 12)
+out["producer: slot free -> TMA issued"] = d(0, 14)
 e = t[lo:hi, :]
 e = e[(e[:, 8] > 0) & (e[:, 9] > 0)]
 if len(e):
