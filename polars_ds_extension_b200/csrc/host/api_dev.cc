@@ -33,6 +33,13 @@ int pdsb_dev_moments_f32(const float* X, int64_t ldx, const float* Y, int64_t ld
   cudaStream_t s = (cudaStream_t)stream;
   const int forced = g_forced_path.load();
   t_last_moments_path = 0;
+  // few features, one target, no mask / weights: the register-moments kernel is HBM-bound where the tensor-core kernel
+  // is bound by its per-stage cost (path 3 in pdsb_last_moments_path)
+  if (!w && !mask && forced == 0 && t == 1 && p <= 10 && n >= 65536) {
+    int rc = moments_small<float>(X, ldx, Y, n, p, M, s);
+    if (rc == 0) { t_last_moments_path = 3; return 0; }
+    if (rc > 0) return rc;
+  }
   if (!w && forced != 1 && moments_tcgen05_supported(X, ldx, Y, ldy, n, p, t)) {
     int rc = moments_tcgen05_f32(X, ldx, Y, ldy, mask, n, p, t, M, s);
     if (rc == 0) { t_last_moments_path = 1; return 0; }

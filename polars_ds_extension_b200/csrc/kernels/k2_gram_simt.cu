@@ -544,9 +544,10 @@ static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64
   const int nb = (q1 + 7) / 8;
   if (!enabled || nb < 1 || nb > 8 || n < 1) return -1;
   // staged kernel for the whole 128-row tiles (needs 16-byte aligned columns), direct kernel for the rest
-  // PDSB_K2A_KERNEL: 16 (default) = m16n8k8 direct, 8 = m8n8k4 direct, 0 = bulk-copy staged m8n8k4 (+ m8n8k4 tail).
-  // Measured (B200, 2e7 x 33 f64): staged 22.9 %, m8n8k4 direct 33.4 % of the HBM peak — see profiles/README.md.
-  static const int kern = [] { const char* e = getenv("PDSB_K2A_KERNEL"); return e ? atoi(e) : 16; }();
+  // PDSB_K2A_KERNEL: 8 (default) = m8n8k4 direct, 16 = m16n8k8 direct, 0 = bulk-copy staged m8n8k4 (+ m8n8k4 tail).
+  // Measured in one call (B200, 2e7 x 33 f64 / 5e7 x 9 f64, profiles/r02/k2a_f64.txt): m8n8k4 direct 33.4 % / 30.0 % of the
+  // HBM peak, m16n8k8 direct 26.3 % / 24.6 %, staged 22.9 % / 31.0 %.
+  static const int kern = [] { const char* e = getenv("PDSB_K2A_KERNEL"); return e ? atoi(e) : 8; }();
   const bool staged_on = kern == 0;
   const int ncol = p + t + (w ? 1 : 0) + (mask ? 1 : 0);
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };

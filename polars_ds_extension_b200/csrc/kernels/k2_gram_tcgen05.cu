@@ -691,40 +691,48 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 }
 
 // Sum the per-CTA partials in a fixed order (bit-reproducible), X'X[a][b] = HH[a][b] + LH[a][b] + LH[b][a], and lay the
-// moments out in the order [X | Y | 1].  One thread per element of the upper triangle, mirrored -> exactly symmetric.
-__global__ void gram_finalize_kernel(const double* __restrict__ partials, const double* __restrict__ xside,
-                                     const double* __restrict__ yside, int nparts, int N, int T, int p, int t, int64_t n,
-                                     int masked, double* __restrict__ M) {
+// moments out in the order [X | Y | 1].  One WARP per element of the upper triangle (mirrored -> exactly symmetric): lane
+// l sums parts l, l + 32, ..., then a fixed-order xor tree.  (One thread per element walking all 148 parts took 0.31 ms —
+// 6 % of the C2 step; this takes a few microseconds.)
+__global__ void __launch_bounds__(256)
+gram_finalize_kernel(const double* __restrict__ partials, const double* __restrict__ xside, const double* __restrict__ yside,
+                     int nparts, int N, int T, int p, int t, int64_t n, int masked, double* __restrict__ M) {
   const int q1 = p + t + 1;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (idx >= q1 * q1) return;
-  int i = idx / q1, j = idx % q1;
+  const int i = idx / q1, j = idx % q1;
   if (i > j) return;
-  auto sum_d = [&](int lanei, int col) { double s = 0.0; for (int k = 0; k < nparts; ++k) s += partials[((size_t)k * 128 + lanei) * N + col]; return s; };
-  double r;
+  double r = 0.0;
   if (j < p) {                                     // X'X
-    const double hh = 0.5 * (sum_d(hi_lane(i), j) + sum_d(hi_lane(j), i));
-    r = hh + sum_d(hi_lane(i) + 16, j) + sum_d(hi_lane(j) + 16, i);
-  } else if (i < p) {                              // X'y_k (slot k) and the column sums (slot T) from the converter lanes
-    const int slot = (j < p + t) ? j - p : T;
-    r = 0.0;
-    for (int k = 0; k < nparts * SIDE_SLOTS; ++k) r += xside[((size_t)k * (T + 1) + slot) * XSIDE_COLS + i];
-  } else {
-    // y / ones block from the side lanes
-    double sy[MAX_T] = {0, 0, 0, 0}, syy[MAX_T] = {0, 0, 0, 0}, cnt = 0.0, cross = 0.0;
-    const bool want_cross = (j < p + t) && (i != j);
-    for (int k = 0; k < nparts * SIDE_SLOTS; ++k) {
-      const double* ys = yside + (size_t)k * YSIDE_STRIDE;
-      for (int u = 0; u < t; ++u) { sy[u] += ys[u * 3 + 0]; syy[u] += ys[u * 3 + 1]; }
-      cnt += ys[2];
-      if (want_cross) cross += ys[12 + (i - p) * 4 + (j - p)];
+    const int li = hi_lane(i), lj = hi_lane(j);
+    double hh = 0.0, hh_t = 0.0, lh_ij = 0.0, lh_ji = 0.0;
+    for (int k = lane; k < nparts; k += 32) {
+      const double* P = partials + (size_t)k * 128 * N;
+      hh += P[(size_t)li * N + j];
+      hh_t += P[(size_t)lj * N + i];
+      lh_ij += P[(size_t)(li + 16) * N + j];
+      lh_ji += P[(size_t)(lj + 16) * N + i];
     }
-    const double count = masked ? cnt : (double)n;
-    if (j == p + t) r = (i == p + t) ? count : sy[i - p];
-    else r = (i == j) ? syy[i - p] : cross;         // y_i . y_j (exact products, f64 across stages)
+    r = 0.5 * (hh + hh_t) + (lh_ij + lh_ji);      // per lane; the lanes are added below
+  } else if (i < p) {                              // X'y_k (slot k) and the column sums (slot T) from the side sums
+    const int slot = (j < p + t) ? j - p : T;
+    for (int k = lane; k < nparts * SIDE_SLOTS; k += 32) r += xside[((size_t)k * (T + 1) + slot) * XSIDE_COLS + i];
+  } else {
+    // y / ones block from the side lanes: [3u+0] sum y_u, [3u+1] sum y_u^2, [2] count, [12 + 4a + b] y_a . y_b
+    const int a = i - p, bb = j - p;
+    int off;
+    if (j == p + t) off = (i == p + t) ? 2 : a * 3 + 0;
+    else off = (i == j) ? a * 3 + 1 : 12 + a * 4 + bb;
+    if (!(j == p + t && i == p + t && !masked))
+      for (int k = lane; k < nparts * SIDE_SLOTS; k += 32) r += yside[(size_t)k * YSIDE_STRIDE + off];
   }
-  M[(size_t)i * q1 + j] = r;
-  M[(size_t)j * q1 + i] = r;
+  for (int off = 16; off; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+  if (j == p + t && i == p + t && !masked) r = (double)n;
+  if (lane == 0) {
+    M[(size_t)i * q1 + j] = r;
+    M[(size_t)j * q1 + i] = r;
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -863,7 +871,7 @@ int moments_tcgen05_core(const Geometry& geo, const float* mask, int64_t n, int 
 #undef PDSB_GO
   if (!rc) {
     const int q1 = p + t + 1;
-    gram_finalize_kernel<<<(q1 * q1 + 127) / 128, 128, 0, s>>>(partials, xside, yside, grid, N, T, p, t, n, mask ? 1 : 0, M);
+    gram_finalize_kernel<<<(q1 * q1 + 7) / 8, 256, 0, s>>>(partials, xside, yside, grid, N, T, p, t, n, mask ? 1 : 0, M);   // 8 warps = 8 elements per block
     cudaError_t e = cudaGetLastError();
     count_launch();
     if (e != cudaSuccess) { set_error("gram finalize launch failed: %s", cudaGetErrorString(e)); rc = 1; }

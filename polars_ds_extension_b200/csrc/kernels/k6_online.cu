@@ -145,8 +145,10 @@ __device__ __forceinline__ void walk_batch(const double* __restrict__ ee, const 
     if (STORE) {
 #pragma unroll
       for (int m = 0; m < TPL; ++m) {
-        gs[r * GS + k0[m]] = (T)W[m][0];
-        gs[r * GS + k1[m]] = (T)W[m][1];
+        // products no moment wants (slot NM) are not stored: several lanes would write that slot, harmlessly, but
+        // compute-sanitizer's racecheck reports every one of them as a WAW hazard
+        if (k0[m] < MomN<D>::NM) gs[r * GS + k0[m]] = (T)W[m][0];
+        if (k1[m] < MomN<D>::NM) gs[r * GS + k1[m]] = (T)W[m][1];
       }
       if (cnt_lane) cnt[r] = W[(NT - 1) / 32][(D + 1) & 1];     // the row count stays exact in f64
     }
@@ -163,9 +165,13 @@ chain_sums_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y,
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t k = (int64_t)blockIdx.x * WARPS + wid;
   if (k >= nchains) return;
-  double v[NM];
+  // Accumulation in the DATA type inside a lane (32 rows of the chain per lane), f64 across lanes: for f32 data the
+  // per-lane sums are 32-term f32 FMA chains — the same precision pass C's scan works in, and a window only ever sees the
+  // DIFFERENCE of a few chain sums, so the error does not grow with n.  (With f64 products this pass ran at 1.36 ms per
+  // 1e8 x 9 f32 = 40 % of the HBM peak: 45 DFMA + 9 conversions per row on a part whose FP64 pipe is narrow.)
+  T v[NM];
 #pragma unroll
-  for (int c = 0; c < NM; ++c) v[c] = 0.0;
+  for (int c = 0; c < NM; ++c) v[c] = T(0);
   const int64_t chain0 = k * CHAIN_ROWS;
   // The pass is a pure stream (read (p+1) s bytes per row, keep NM sums): what bounds it is bytes in flight.  ncu, round
   // 2: with one 32-row batch of loads per warp outstanding the kernel sat at 25 % of the HBM peak (2.1 ms per 1e8 x 9
@@ -188,23 +194,22 @@ chain_sums_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y,
 #pragma unroll
       for (int c = 0; c < D; ++c) acc = fma(z[c], T(0), acc);
       const bool fin = (r < n) && (acc == T(0));
-      double dz[D];
 #pragma unroll
-      for (int c = 0; c < D; ++c) dz[c] = fin ? (double)z[c] : 0.0;
-      const double dy = fin ? (double)yv : 0.0;
+      for (int c = 0; c < D; ++c) z[c] = fin ? z[c] : T(0);
+      yv = fin ? yv : T(0);
       int q = 0;
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
-        for (int jj = i; jj < D; ++jj) { v[q] = fma(dz[i], dz[jj], v[q]); ++q; }
+        for (int jj = i; jj < D; ++jj) { v[q] = fma(z[i], z[jj], v[q]); ++q; }
 #pragma unroll
-      for (int i = 0; i < D; ++i) { v[q] = fma(dz[i], dy, v[q]); ++q; }
-      v[q] += fin ? 1.0 : 0.0;
+      for (int i = 0; i < D; ++i) { v[q] = fma(z[i], yv, v[q]); ++q; }
+      v[q] += fin ? T(1) : T(0);
     }
   }
 #pragma unroll
   for (int c = 0; c < NM; ++c) {
-    double x = v[c];
+    double x = (double)v[c];
 #pragma unroll
     for (int off = 16; off; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
     if (lane == (c & 31)) S[(size_t)c * nchains + k] = x;

@@ -58,6 +58,10 @@ template <typename T>
 int grouped_lin_reg(const T* X, int64_t ldx, const T* y, const int64_t* offsets, int64_t n_groups,
                     int64_t n, int p, const pdsb_solve_opts& o, double* beta, int* status, cudaStream_t s);
 
+// whole-frame moments for p <= 10 features and one target on K5's register kernel (0 ok, 1 error, -1 shape not taken)
+template <typename T>
+int moments_small(const T* X, int64_t ldx, const T* y, int64_t n, int p, double* M, cudaStream_t s);
+
 // K6/K7 rolling + recursive
 template <typename T>
 int online_lin_reg(const T* X, int64_t ldx, const T* y, int64_t n, int p, int add_bias, int64_t window,

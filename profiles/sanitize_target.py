@@ -41,6 +41,10 @@ for f64 in (False, True):
     gpu.eval(df, pds.lin_reg_report(*xs, target="y", add_bias=True, std_err="hc3"))
     gpu.eval(df, pds.lin_reg(*xs, target="y", l1_reg=0.01, add_bias=True))
     gpu.eval(df, pds.lin_reg(*xs, target="y", positive=True))
+    gpu.eval(df, pds.lin_reg(*xs, target=["y", "x0", "x1"], add_bias=True))        # multi-target: side sums for t > 1
+    if f64:
+        yb = (rng.random(5000) < 0.5).astype(np.float64)
+        gpu.eval(df.with_columns(yb=yb), pds.logistic_reg(*xs, target="yb", max_iter=5))       # K11 + weighted K2a + K3
     gid = np.repeat(np.arange(10), 500)
     gpu.group_eval(df.with_columns(g=gid), "g", pds.lin_reg(*xs, target="y", add_bias=True), fast=True)
     gpu.group_eval(df.with_columns(g=gid), "g", pds.lin_reg(*xs, target="y", l1_reg=0.01), fast=True)

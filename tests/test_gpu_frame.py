@@ -34,10 +34,10 @@ def test_frame_moments_and_predict(n, p, t, order):
     scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
     Mf = dev.moments_frame(frame, n, p + t, xcol, p, ycol, t).cpu().numpy()
     used_tc = lib().pdsb_last_moments_path() == 1
-    # tensor-core path: Z~ <= 64 columns (raw-hi kernel) or p <= 64 with the features-only A operand (N <= 80)
-    assert used_tc == (n >= 4096 and p <= 64 and (p + t + 1 <= 64 or p + 2 * t + 1 <= 80))
+    # tensor-core path: up to 64 features on the tensor core, up to 4 targets on the side lanes
+    assert used_tc == (n >= 4096 and p <= 64 and t <= 4)
     Mc = dev.moments(X, Y, n=n).cpu().numpy()
-    assert np.isfinite(Mf).all()          # every block is produced, including y_i . y_j (i != j) of the features-only variant
+    assert np.isfinite(Mf).all()          # every block is produced, including y_i . y_j (i != j) from the side lanes
     assert np.max(np.abs(Mf - ref) / scale) < 3e-6
     if used_tc:
         assert np.array_equal(Mf, Mc, equal_nan=True)      # same kernel, same stage order: the layout must not change a single bit
