@@ -92,7 +92,8 @@ int pdsb_dev_allreduce_f64(double* buf, int64_t count, void* stream);
 /* bytes of the calling thread's last host-layer upload that went through the pinned staging ring (pageable input) */
 int64_t pdsb_last_staged_bytes(void);
 
-/* tcgen05 kernel variant: 1 raw-hi (default; B operand = raw TMA tile, hardware truncation), 0 explicit-hi cross-check */
+/* tcgen05 kernel variant: 1 (default) the hi lanes of the A operand hold the raw data (the tensor core truncates fp32
+ * to TF32 itself), 0 they clear the low 13 mantissa bits themselves (cross-check: must be bit-identical) */
 void pdsb_set_tc_variant(int v);
 
 /* =====================================================================================================

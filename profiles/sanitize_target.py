@@ -28,9 +28,9 @@ def frame(n, p, dt):
 for f64 in (False, True):
     cfg.LIN_REG_EXPR_F64 = f64
     dt = np.float64 if f64 else np.float32
-    df, xs = frame(9000, 32, dt)                       # tcgen05 raw-hi (f32) / staged DMMA (f64)
+    df, xs = frame(9000, 32, dt)                       # tcgen05 kernel with side warps (f32) / DMMA (f64)
     gpu.eval(df, pds.lin_reg(*xs, target="y", return_pred=True))
-    df, xs = frame(8200, 64, dt)                       # features-only tcgen05 kernel (f32)
+    df, xs = frame(8200, 64, dt)                       # tcgen05 kernel, 4 quadrants, converter-side sums (f32)
     gpu.eval(df, pds.lin_reg(*xs, target="y", add_bias=True))
     df, xs = frame(5000, 8, dt)
     gpu.eval(df, pds.rolling_lin_reg(*xs, target="y", window_size=1024))       # packed f32x2 / lane-per-moment
