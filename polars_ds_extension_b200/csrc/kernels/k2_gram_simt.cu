@@ -262,6 +262,121 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, const double* __rest
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Wide variant: the direct kernel keeps 4 rows x (p + t) x 8 B in flight per warp and measured 33 % of the HBM peak with
+// the DMMA pipe at 43 % of ITS measured peak (profiles/fp64_peak.cu: 37 TFLOP/s for every mma.sync f64 shape, 33 for
+// DFMA) — it waits on memory latency, not on issue slots.  Here a lane loads TWO consecutive rows (16 bytes) per column
+// block: lane (g, k) reads rows r0 + 2k, r0 + 2k + 1 of column 8b + g, an 8-row batch per warp.  The rows of a DMMA's
+// k index can be any four rows, so the .x halves (rows r0 + {0, 2, 4, 6}) make one m8n8k4 step and the .y halves the
+// next.  DEPTH batches live in a register ring (the loop is unrolled over the ring, so every index is static): DEPTH - 1
+// batches = 8 (DEPTH - 1) rows per warp are in flight while one is multiplied.  The mask is just the "ones" column read
+// from memory.  128-thread CTAs, MINB per SM.  Needs 16-byte aligned columns and even leading dimensions.
+template <int NB, int DEPTH, int MINB, bool WEIGHTED>
+__global__ void __launch_bounds__(128, MINB)
+gram_dmma_wide_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
+                      const double* __restrict__ w, const double* __restrict__ mask, int64_t n, int p, int t,
+                      double* __restrict__ partials /* [grid][q1*q1] */) {
+  constexpr int NP = NB * (NB + 1) / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);      // [NP][64]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, k = lane & 3;
+  const int q1 = p + t + 1;
+  const double* colp[NB];
+  int kind[NB];                                           // 0 load, 1 ones, 2 zero padding
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int c = 8 * b + g;
+    kind[b] = c < p + t ? 0 : (c == p + t ? (mask ? 0 : 1) : 2);
+    colp[b] = c < p ? X + (int64_t)c * ldx : (c < p + t ? Y + (int64_t)(c - p) * ldy : (mask ? mask : X));
+  }
+  double acc[NP][2];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+
+  double2 buf[DEPTH][NB];
+  double2 wb[DEPTH];
+  const int64_t S = (int64_t)gridDim.x * 4 * 8;
+  const int64_t r0 = ((int64_t)blockIdx.x * 4 + warp) * 8;
+  int64_t rl = r0 + 2 * k;                                // this lane's first row of the NEXT batch to load
+  const double* wp = WEIGHTED ? w + rl : nullptr;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) colp[b] += rl;
+  auto load_batch = [&](double2* z, double2& wv) {        // n is a multiple of 8 here: a batch is all in or all out
+    const bool in = rl < n;
+    if constexpr (WEIGHTED) {
+      wv = make_double2(0.0, 0.0);
+      if (in) wv = __ldcs(reinterpret_cast<const double2*>(wp));
+      wp += S;
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      double2 v = make_double2(0.0, 0.0);
+      if (in) {
+        if (kind[b] == 0) v = __ldcs(reinterpret_cast<const double2*>(colp[b]));
+        else if (kind[b] == 1) v = make_double2(1.0, 1.0);
+      }
+      z[b] = v;
+      colp[b] += S;
+    }
+    rl += S;
+  };
+  auto multiply = [&](const double2* z, const double2& wv) {
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const double a0 = WEIGHTED ? z[i].x * wv.x : z[i].x;
+      const double a1 = WEIGHTED ? z[i].y * wv.y : z[i].y;
+#pragma unroll
+      for (int j = i; j < NB; ++j) {
+        dmma884(acc[idx][0], acc[idx][1], a0, z[j].x);
+        dmma884(acc[idx][0], acc[idx][1], a1, z[j].y);
+        ++idx;
+      }
+    }
+  };
+
+#pragma unroll
+  for (int d = 0; d < DEPTH - 1; ++d) load_batch(buf[d], wb[d]);
+  for (int64_t rc = r0; rc < n; rc += DEPTH * S) {
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) {
+      load_batch(buf[(d + DEPTH - 1) % DEPTH], wb[(d + DEPTH - 1) % DEPTH]);
+      multiply(buf[d], wb[d]);
+    }
+  }
+  // ---- CTA reduction in a fixed order: warp 0 stores, warps 1..3 add one after the other ----
+  for (int wturn = 0; wturn < 4; ++wturn) {
+    if (warp == wturn) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        double* d = sm + i * 64 + g * 8 + 2 * k;
+        if (wturn == 0) { d[0] = acc[i][0]; d[1] = acc[i][1]; }
+        else { d[0] += acc[i][0]; d[1] += acc[i][1]; }
+      }
+    }
+    __syncthreads();
+  }
+  double* out = partials + (size_t)blockIdx.x * q1 * q1;
+  for (int e = threadIdx.x; e < NP * 64; e += 128) {
+    const int blk = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+    int i = 0, rem = blk;
+    while (rem >= NB - i) { rem -= NB - i; ++i; }
+    const int j = i + rem;
+    const int a = 8 * i + rr, b = 8 * j + cc;
+    if (a < q1 && b < q1 && (i != j || a <= b)) {
+      const double v = sm[e];
+      out[(size_t)a * q1 + b] = v;
+      out[(size_t)b * q1 + a] = v;
+    }
+  }
+}
+
+template <int NB> struct WideCfg {
+  static constexpr int DEPTH = NB <= 2 ? 6 : (NB <= 4 ? 4 : (NB == 5 ? 3 : 2));
+  static constexpr int MINB = NB <= 2 ? 4 : (NB <= 6 ? 3 : 2);
+};
+
+// ------------------------------------------------------------------------------------------------------------
 // Staged variant (the production f64 path for n >= 4096 rows): the direct kernel above loads one 8-byte scalar per lane
 // and 4-row step, i.e. eight 32-byte sectors of eight different columns per load instruction, with 4 rows in flight per
 // warp — 33 % of the HBM peak at 33 columns (round 1).  Here every CTA streams 128-row tiles: one elected thread issues a
@@ -536,6 +651,17 @@ static int launch_dmma(const double* X, int64_t ldx, const double* Y, int64_t ld
   return 0;
 }
 
+template <int NB>
+static int launch_dmma_wide(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w, const double* mask,
+                            int64_t n, int p, int t, int grid, double* partials, cudaStream_t s) {
+  const size_t smem = (size_t)(NB * (NB + 1) / 2) * 64 * sizeof(double);
+  if (w) gram_dmma_wide_kernel<NB, WideCfg<NB>::DEPTH, WideCfg<NB>::MINB, true><<<grid, 128, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, partials);
+  else gram_dmma_wide_kernel<NB, WideCfg<NB>::DEPTH, WideCfg<NB>::MINB, false><<<grid, 128, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, partials);
+  PDSB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
 // 0 ok, 1 error, -1 not applicable (caller uses the DFMA kernel).  PDSB_K2A_DMMA=0 disables.
 static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w,
                             const double* mask, int64_t n, int p, int t, double* M, cudaStream_t s) {
@@ -547,7 +673,7 @@ static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64
   // PDSB_K2A_KERNEL: 8 (default) = m8n8k4 direct, 16 = m16n8k8 direct, 0 = bulk-copy staged m8n8k4 (+ m8n8k4 tail).
   // Measured in one call (B200, 2e7 x 33 f64 / 5e7 x 9 f64, profiles/r02/k2a_f64.txt): m8n8k4 direct 33.4 % / 30.0 % of the
   // HBM peak, m16n8k8 direct 26.3 % / 24.6 %, staged 22.9 % / 31.0 %.
-  static const int kern = [] { const char* e = getenv("PDSB_K2A_KERNEL"); return e ? atoi(e) : 8; }();
+  static const int kern = [] { const char* e = getenv("PDSB_K2A_KERNEL"); return e ? atoi(e) : 2; }();
   const bool staged_on = kern == 0;
   const int ncol = p + t + (w ? 1 : 0) + (mask ? 1 : 0);
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -555,10 +681,12 @@ static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64
   const size_t tile_bytes = (size_t)ncol * DT_RP * sizeof(double);
   int stages = (int)std::min<size_t>(4, (200 * 1024 - 256) / tile_bytes);
   const size_t red_bytes = (size_t)(nb * (nb + 1) / 2) * 64 * sizeof(double);
+  const bool wide = kern == 2 && aligned && n >= 8;       // whole 8-row batches; the last n % 8 rows go to the direct kernel
   const int64_t ntiles = (staged_on && aligned && stages >= 2 && n >= 4096) ? n / DT_R : 0;
-  const int64_t n_main = ntiles * DT_R;
+  const int64_t n_main = wide ? n - n % 8 : ntiles * DT_R;
   const int64_t n_tail = n - n_main;
   int grid_main = 0, grid = 0;
+  if (wide) grid_main = (int)std::min<int64_t>(ceil_div(n_main, 32), (int64_t)sm_count() * (nb <= 2 ? 4 : (nb <= 6 ? 3 : 2)));
   if (ntiles > 0) {
     // one or two CTAs per SM, whatever shared memory allows
     const size_t smem_need = std::max((size_t)stages * tile_bytes, red_bytes) + 2 * stages * sizeof(uint64_t) + 128;
@@ -573,7 +701,19 @@ static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64
   double* partials = nullptr;
   if (dev_alloc((void**)&partials, (size_t)(grid_main + grid) * q1 * q1 * sizeof(double), s)) return 1;
   int rc = 0;
-  if (grid_main > 0) {
+  if (wide) {
+    switch (nb) {
+      case 1: rc = launch_dmma_wide<1>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
+      case 2: rc = launch_dmma_wide<2>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
+      case 3: rc = launch_dmma_wide<3>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
+      case 4: rc = launch_dmma_wide<4>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
+      case 5: rc = launch_dmma_wide<5>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
+      case 6: rc = launch_dmma_wide<6>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
+      case 7: rc = launch_dmma_wide<7>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
+      default: rc = launch_dmma_wide<8>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
+    }
+    if (rc) { dev_free(partials, s); return rc; }
+  } else if (grid_main > 0) {
     const size_t smem = std::max((size_t)stages * tile_bytes, red_bytes) + 2 * stages * sizeof(uint64_t) + 128;
 #define PDSB_ST(NBV) rc = launch_dmma_staged<NBV>(X, ldx, Y, ldy, w, mask, ntiles, p, t, grid_main, stages, smem, partials, s)
     switch (nb) {
