@@ -321,17 +321,20 @@ gram_dmma_wide_kernel(const double* __restrict__ X, int64_t ldx, const double* _
     rl += S;
   };
   auto multiply = [&](const double2* z, const double2& wv) {
+    // all block pairs for the even rows, then all for the odd rows: consecutive DMMAs never share an accumulator
     int idx = 0;
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
       const double a0 = WEIGHTED ? z[i].x * wv.x : z[i].x;
+#pragma unroll
+      for (int j = i; j < NB; ++j) { dmma884(acc[idx][0], acc[idx][1], a0, z[j].x); ++idx; }
+    }
+    idx = 0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
       const double a1 = WEIGHTED ? z[i].y * wv.y : z[i].y;
 #pragma unroll
-      for (int j = i; j < NB; ++j) {
-        dmma884(acc[idx][0], acc[idx][1], a0, z[j].x);
-        dmma884(acc[idx][0], acc[idx][1], a1, z[j].y);
-        ++idx;
-      }
+      for (int j = i; j < NB; ++j) { dmma884(acc[idx][0], acc[idx][1], a1, z[j].y); ++idx; }
     }
   };
 
@@ -371,115 +374,121 @@ gram_dmma_wide_kernel(const double* __restrict__ X, int64_t ldx, const double* _
   }
 }
 
-template <int NB> struct WideCfg {
-  static constexpr int DEPTH = NB <= 2 ? 6 : (NB <= 4 ? 4 : (NB == 5 ? 3 : 2));
-  static constexpr int MINB = NB <= 2 ? 4 : (NB <= 6 ? 3 : 2);
-};
-
-// ------------------------------------------------------------------------------------------------------------
-// Staged variant (the production f64 path for n >= 4096 rows): the direct kernel above loads one 8-byte scalar per lane
-// and 4-row step, i.e. eight 32-byte sectors of eight different columns per load instruction, with 4 rows in flight per
-// warp — 33 % of the HBM peak at 33 columns (round 1).  Here every CTA streams 128-row tiles: one elected thread issues a
-// 1-D bulk async copy (cp.async.bulk, the TMA engine) per column — 1 KiB contiguous each — into a shared-memory tile
-// [column][132] (pitch 132 doubles: the 8-column x 4-row fragment read of a warp is bank-conflict-free), completion on an
-// mbarrier ring of STAGES tiles.  Warps take 16 rows of a tile each: per 4-row step NB LDS.64 feed the same
-// NB (NB + 1) / 2 DMMAs as before.  Rows in flight per CTA: STAGES x 128.  Only whole 128-row tiles are handled here; the
-// tail (< 128 rows) goes through the direct kernel into further partials, and a fixed-order reduce joins both.
-constexpr int DT_R = 128;                 // rows per tile
-constexpr int DT_RP = 132;                // pitch in doubles (132 * 8 B = 32 B mod 128 B)
-
-__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <int NB>
-__global__ void __launch_bounds__(256)
-gram_dmma_staged_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
-                        const double* __restrict__ w, const double* __restrict__ mask, int64_t ntiles, int p, int t,
-                        int stages, double* __restrict__ partials /* [grid][q1*q1] */) {
+// Single-target variant of the wide kernel: only the FEATURE columns go through the tensor-core blocks (NB = ceil(p / 8));
+// the products with y, the column sums and y'y / sum(y) / count are lane-local DFMAs on the same registers (a lane owns
+// two rows of one column per block, and loads y / mask / weight for exactly those two rows — the 8 lanes that share k read
+// the same 16 bytes).  p = 32 needs 10 block pairs instead of the 15 that [X | y | 1] = 34 -> 40 columns cost, p = 8 one
+// instead of 3: the DMMA pipe (37 TFLOP/s measured) is the bound of this path, so the padding columns were the waste.
+// AUX = weights and / or mask present (a missing one is loaded as ones).
+template <int NB, int DEPTH, int MINB, bool AUX>
+__global__ void __launch_bounds__(128, MINB)
+gram_dmma_side_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ y,
+                      const double* __restrict__ w, const double* __restrict__ mask, int64_t n, int p,
+                      double* __restrict__ partials /* [grid][(p+2)^2] */) {
   constexpr int NP = NB * (NB + 1) / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int ncol = p + t + (w ? 1 : 0) + (mask ? 1 : 0);       // staged columns: data, then weights, then mask
-  const int wcol = p + t, mcol = p + t + (w ? 1 : 0);
-  const size_t tile_doubles = (size_t)ncol * DT_RP;
-  double* tiles = reinterpret_cast<double*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)stages * tile_doubles);
-  uint64_t* empty = full + stages;
-  double* sm = tiles;                                          // reused for the CTA reduction after the main loop
+  double* sm = reinterpret_cast<double*>(smem_raw);      // [NP][64] blocks, then [NB * 8][2] (x.y, sum x), then 3 scalars
+  double* sside = sm + NP * 64;
+  double* sscal = sside + NB * 16;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, k = lane & 3;
-  const int q1 = p + t + 1;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < stages; ++i) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(&full[i])), "r"(1));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(&empty[i])), "r"(8));
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const uint32_t my_tiles = ntiles > (int64_t)blockIdx.x ? (uint32_t)((ntiles - 1 - blockIdx.x) / gridDim.x + 1) : 0u;
-  auto issue = [&](uint32_t it) {      // one thread: all columns of tile `it` of this CTA -> stage it % stages
-    const int st = it % stages;
-    const int64_t r0 = ((int64_t)it * gridDim.x + blockIdx.x) * DT_R;
-    const uint32_t bar = smem_addr_u32(&full[st]);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(ncol * DT_R * 8)) : "memory");
-    double* dst = tiles + (size_t)st * tile_doubles;
-    for (int c = 0; c < ncol; ++c) {
-      const double* src = c < p ? X + (int64_t)c * ldx + r0 : (c < p + t ? Y + (int64_t)(c - p) * ldy + r0 : ((w && c == wcol) ? w + r0 : mask + r0));
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(smem_addr_u32(dst + (size_t)c * DT_RP)), "l"(src), "r"((uint32_t)(DT_R * 8)), "r"(bar) : "memory");
-    }
-  };
-  auto wait = [&](uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spins = 0; !done; ++spins) {
-      asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
-                   : "=r"(done) : "r"(smem_addr_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
-      if (!done && spins > (1u << 24)) __trap();
-    }
-  };
-  if (threadIdx.x == 0)
-    for (uint32_t it = 0; it < my_tiles && it < (uint32_t)stages; ++it) issue(it);
-
-  int kind[NB], cidx[NB];                 // 0 data column cidx, 1 ones / mask, 2 zero padding
+  const int q1 = p + 2;
+  const double* colp[NB];
+  bool live[NB];
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     const int c = 8 * b + g;
-    kind[b] = c < p + t ? 0 : (c == p + t ? 1 : 2);
-    cidx[b] = c < p + t ? c : 0;
+    live[b] = c < p;
+    colp[b] = X + (int64_t)(live[b] ? c : 0) * ldx;
   }
   double acc[NP][2];
 #pragma unroll
   for (int i = 0; i < NP; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  double xy[NB], x1[NB], yy = 0.0, y1 = 0.0, c11 = 0.0;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) { xy[b] = 0.0; x1[b] = 0.0; }
 
-  for (uint32_t it = 0; it < my_tiles; ++it) {
-    const int st = it % stages;
-    const uint32_t ph = (it / stages) & 1;
-    wait(&full[st], ph);
-    const double* tile = tiles + (size_t)st * tile_doubles;
+  struct Batch { double2 z[NB]; double2 y, w, m; };
+  Batch ring[DEPTH];
+  const int64_t S = (int64_t)gridDim.x * 4 * 8;
+  const int64_t r0 = ((int64_t)blockIdx.x * 4 + warp) * 8;
+  int64_t rl = r0 + 2 * k;
+  const double* yp = y + rl;
+  const double* wp = (AUX && w) ? w + rl : nullptr;
+  const double* mp = (AUX && mask) ? mask + rl : nullptr;
 #pragma unroll
-    for (int step = 0; step < 4; ++step) {
-      const int r = warp * 16 + step * 4 + k;
-      double z[NB];
-      const double mk = mask ? tile[(size_t)mcol * DT_RP + r] : 1.0;
-      const double wv = w ? tile[(size_t)wcol * DT_RP + r] : 1.0;
-#pragma unroll
-      for (int b = 0; b < NB; ++b) z[b] = kind[b] == 0 ? tile[(size_t)cidx[b] * DT_RP + r] : (kind[b] == 1 ? mk : 0.0);
-      int idx = 0;
-#pragma unroll
-      for (int i = 0; i < NB; ++i) {
-        const double a = z[i] * wv;
-#pragma unroll
-        for (int j = i; j < NB; ++j) { dmma884(acc[idx][0], acc[idx][1], a, z[j]); ++idx; }
-      }
+  for (int b = 0; b < NB; ++b) colp[b] += rl;
+  auto load_batch = [&](Batch& q) {                       // n is a multiple of 8 here: a batch is all in or all out
+    const bool in = rl < n;
+    const double2 zero = make_double2(0.0, 0.0), one = make_double2(1.0, 1.0);
+    q.y = in ? __ldcs(reinterpret_cast<const double2*>(yp)) : zero;
+    yp += S;
+    if constexpr (AUX) {
+      q.w = in ? (wp ? __ldcs(reinterpret_cast<const double2*>(wp)) : one) : zero;
+      q.m = in ? (mp ? __ldcs(reinterpret_cast<const double2*>(mp)) : one) : zero;
+      if (wp) wp += S;
+      if (mp) mp += S;
+    } else {
+      q.m = in ? one : zero;
     }
-    __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(&empty[st])) : "memory");
-    if (threadIdx.x == 0 && it + stages < my_tiles) {     // refill this stage once all 8 warps have left it
-      wait(&empty[st], ph);
-      issue(it + stages);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      q.z[b] = (in && live[b]) ? __ldcs(reinterpret_cast<const double2*>(colp[b])) : zero;
+      colp[b] += S;
+    }
+    rl += S;
+  };
+  auto multiply = [&](const Batch& q) {
+    double2 wy, wm;                                        // w y, w m (the weight enters every product once)
+    if constexpr (AUX) { wy = make_double2(q.w.x * q.y.x, q.w.y * q.y.y); wm = make_double2(q.w.x * q.m.x, q.w.y * q.m.y); }
+    else { wy = q.y; wm = q.m; }
+    yy = fma(wy.x, q.y.x, fma(wy.y, q.y.y, yy));
+    y1 = fma(wy.x, q.m.x, fma(wy.y, q.m.y, y1));
+    c11 = fma(wm.x, q.m.x, fma(wm.y, q.m.y, c11));
+    // all block pairs for the even rows, then all for the odd rows: consecutive DMMAs never share an accumulator
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      xy[i] = fma(q.z[i].x, wy.x, xy[i]);
+      x1[i] = fma(q.z[i].x, wm.x, x1[i]);
+      const double a0 = AUX ? q.z[i].x * q.w.x : q.z[i].x;
+#pragma unroll
+      for (int j = i; j < NB; ++j) { dmma884(acc[idx][0], acc[idx][1], a0, q.z[j].x); ++idx; }
+    }
+    idx = 0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      xy[i] = fma(q.z[i].y, wy.y, xy[i]);
+      x1[i] = fma(q.z[i].y, wm.y, x1[i]);
+      const double a1 = AUX ? q.z[i].y * q.w.y : q.z[i].y;
+#pragma unroll
+      for (int j = i; j < NB; ++j) { dmma884(acc[idx][0], acc[idx][1], a1, q.z[j].y); ++idx; }
+    }
+  };
+
+#pragma unroll
+  for (int d = 0; d < DEPTH - 1; ++d) load_batch(ring[d]);
+  for (int64_t rc = r0; rc < n; rc += DEPTH * S) {
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) {
+      load_batch(ring[(d + DEPTH - 1) % DEPTH]);
+      multiply(ring[d]);
     }
   }
-  __syncthreads();       // every tile consumed: the tile memory becomes the reduction scratch
-  for (int wturn = 0; wturn < 8; ++wturn) {
+  // lane-local sums -> warp sums over the 4 row slots (k); the y / count scalars are the same in all 8 column groups
+#pragma unroll
+  for (int off = 1; off <= 2; off <<= 1) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      xy[b] += __shfl_xor_sync(0xffffffffu, xy[b], off);
+      x1[b] += __shfl_xor_sync(0xffffffffu, x1[b], off);
+    }
+    yy += __shfl_xor_sync(0xffffffffu, yy, off);
+    y1 += __shfl_xor_sync(0xffffffffu, y1, off);
+    c11 += __shfl_xor_sync(0xffffffffu, c11, off);
+  }
+  // ---- CTA reduction in a fixed order: warp 0 stores, warps 1..3 add one after the other ----
+  for (int wturn = 0; wturn < 4; ++wturn) {
     if (warp == wturn) {
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
@@ -487,159 +496,58 @@ gram_dmma_staged_kernel(const double* __restrict__ X, int64_t ldx, const double*
         if (wturn == 0) { d[0] = acc[i][0]; d[1] = acc[i][1]; }
         else { d[0] += acc[i][0]; d[1] += acc[i][1]; }
       }
+      if (k == 0) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          double* d = sside + (b * 8 + g) * 2;
+          if (wturn == 0) { d[0] = xy[b]; d[1] = x1[b]; }
+          else { d[0] += xy[b]; d[1] += x1[b]; }
+        }
+      }
+      if (lane == 0) {
+        if (wturn == 0) { sscal[0] = yy; sscal[1] = y1; sscal[2] = c11; }
+        else { sscal[0] += yy; sscal[1] += y1; sscal[2] += c11; }
+      }
     }
     __syncthreads();
   }
   double* out = partials + (size_t)blockIdx.x * q1 * q1;
-  for (int e = threadIdx.x; e < NP * 64; e += 256) {
+  for (int e = threadIdx.x; e < NP * 64; e += 128) {
     const int blk = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
     int i = 0, rem = blk;
     while (rem >= NB - i) { rem -= NB - i; ++i; }
     const int j = i + rem;
     const int a = 8 * i + rr, b = 8 * j + cc;
-    if (a < q1 && b < q1 && (i != j || a <= b)) {
+    if (a < p && b < p && (i != j || a <= b)) {
       const double v = sm[e];
       out[(size_t)a * q1 + b] = v;
       out[(size_t)b * q1 + a] = v;
     }
   }
+  for (int c = threadIdx.x; c < p; c += 128) {
+    const double vxy = sside[c * 2], vx1 = sside[c * 2 + 1];
+    out[(size_t)c * q1 + p] = vxy;
+    out[(size_t)p * q1 + c] = vxy;
+    out[(size_t)c * q1 + p + 1] = vx1;
+    out[(size_t)(p + 1) * q1 + c] = vx1;
+  }
+  if (threadIdx.x == 0) {
+    out[(size_t)p * q1 + p] = sscal[0];
+    out[(size_t)p * q1 + p + 1] = sscal[1];
+    out[(size_t)(p + 1) * q1 + p] = sscal[1];
+    out[(size_t)(p + 1) * q1 + p + 1] = sscal[2];
+  }
 }
 
-template <int NB>
-static int launch_dmma_staged(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w, const double* mask,
-                              int64_t ntiles, int p, int t, int grid, int stages, size_t smem, double* partials, cudaStream_t s) {
-  auto k = gram_dmma_staged_kernel<NB>;
-  PDSB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<grid, 256, smem, s>>>(X, ldx, Y, ldy, w, mask, ntiles, p, t, stages, partials);
-  PDSB_LAUNCH_OK();
-  count_launch();
-  return 0;
-}
+// ring depth and CTAs per SM (128 threads each) by block count: what fits 65536 registers without spilling in the loop
+constexpr int side_depth(int nb, bool aux) { return aux ? (nb <= 1 ? 5 : (nb <= 2 ? 4 : (nb <= 3 ? 3 : 2))) : (nb <= 1 ? 8 : (nb <= 2 ? 5 : (nb <= 4 ? 3 : 2))); }
+constexpr int side_minb(int nb, bool aux) { return aux ? (nb <= 2 ? 4 : (nb <= 4 ? 3 : 2)) : (nb <= 2 ? 4 : (nb <= 5 ? 3 : 2)); }
+constexpr int wide_minb(int nb) { return nb <= 2 ? 4 : (nb <= 6 ? 3 : 2); }
 
-// ------------------------------------------------------------------------------------------------------------
-// m16n8k8 variant (production): the same data flow as gram_dmma_kernel with the larger FP64 tensor-core shape.
-// An 8-row step gives every lane two elements per 8-column block, Z~[k0 + l%4][8b + l/4] and Z~[k0 + l%4 + 4][8b + l/4];
-// they are the B fragment (8 x 8, "col") of block b and one half of the A fragment (16 x 8, "row") of the block pair
-// that contains b.  A block pair I (16 columns) meets block J (8 columns) in one mma.sync.m16n8k8 (2048 flops); only
-// the pairs that touch the upper triangle (J >= 2 I) are issued: 9 instructions per 8 rows at 33..40 columns, where the
-// m8n8k4 kernel issues 30.  Round 2 measured the m8n8k4 kernel at 33 % of the HBM peak with the FP64 pipe far from its
-// peak: the small shape is issue-limited.
-__device__ __forceinline__ void dmma1688(double* c, double a0, double a1, double a2, double a3, double b0, double b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3]) : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(b0), "d"(b1));
-}
-
-template <int NB> struct Dmma16 {
-  static constexpr int NI = (NB + 1) / 2;                 // 16-column block pairs
-  static constexpr int count() { int c = 0; for (int i = 0; i < NI; ++i) for (int j = 2 * i; j < NB; ++j) ++c; return c; }
-  static constexpr int NMMA = count();
+template <int NB> struct WideCfg {
+  static constexpr int DEPTH = NB <= 2 ? 6 : (NB <= 4 ? 4 : (NB == 5 ? 3 : 2));
+  static constexpr int MINB = wide_minb(NB);
 };
-
-constexpr int D16_WARPS = 4;   // 128-thread CTAs: 152 registers at 33..40 columns -> 3 CTAs (12 warps) per SM
-template <int NB>
-__global__ void __launch_bounds__(D16_WARPS * 32)
-gram_dmma16_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
-                   const double* __restrict__ w, const double* __restrict__ mask, int64_t n, int p, int t,
-                   double* __restrict__ partials /* [grid][q1*q1] */) {
-  constexpr int NI = Dmma16<NB>::NI, NMMA = Dmma16<NB>::NMMA;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sm = reinterpret_cast<double*>(smem_raw);      // [NMMA][128] CTA-level sum of the warps' accumulators
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, k = lane & 3;
-  const int q1 = p + t + 1;
-  const double* colp[NB];
-  int kind[NB];                                           // 0 data, 1 ones / mask, 2 zero padding
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    const int c = 8 * b + g;
-    kind[b] = c < p + t ? 0 : (c == p + t ? 1 : 2);
-    colp[b] = c < p ? X + (int64_t)c * ldx : (c < p + t ? Y + (int64_t)(c - p) * ldy : X);
-  }
-  double acc[NMMA][4];
-#pragma unroll
-  for (int i = 0; i < NMMA; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; acc[i][2] = 0.0; acc[i][3] = 0.0; }
-
-  const int64_t stride = (int64_t)gridDim.x * D16_WARPS * 8;
-  auto load_step = [&](int64_t r0, double (*z)[2], double* wv) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int64_t r = r0 + k + 4 * h;
-      const bool in = r < n;
-      wv[h] = (in && w) ? w[r] : 1.0;
-#pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        double v = 0.0;
-        if (in) {
-          if (kind[b] == 0) v = colp[b][r];
-          else if (kind[b] == 1) v = mask ? mask[r] : 1.0;
-        }
-        z[b][h] = v;
-      }
-    }
-  };
-  int64_t r0 = ((int64_t)blockIdx.x * D16_WARPS + warp) * 8;
-  double z[NB][2], zn[NB][2], wv[2] = {1.0, 1.0}, wn[2] = {1.0, 1.0};
-  if (r0 < n) load_step(r0, z, wv);
-  for (; r0 < n; r0 += stride) {
-    const bool more = r0 + stride < n;
-    if (more) load_step(r0 + stride, zn, wn);             // next step's loads fly while this step's DMMAs issue
-    int idx = 0;
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      // A fragment of the block pair (2i, 2i+1): a0 (row g, k), a1 (row g+8, k), a2 (row g, k+4), a3 (row g+8, k+4)
-      const double a0 = z[2 * i][0] * wv[0], a2 = z[2 * i][1] * wv[1];
-      const double a1 = (2 * i + 1 < NB) ? z[2 * i + 1 < NB ? 2 * i + 1 : 0][0] * wv[0] : 0.0;
-      const double a3 = (2 * i + 1 < NB) ? z[2 * i + 1 < NB ? 2 * i + 1 : 0][1] * wv[1] : 0.0;
-#pragma unroll
-      for (int j = 2 * i; j < NB; ++j) { dmma1688(acc[idx], a0, a1, a2, a3, z[j][0], z[j][1]); ++idx; }
-    }
-    if (more) {
-#pragma unroll
-      for (int b = 0; b < NB; ++b) { z[b][0] = zn[b][0]; z[b][1] = zn[b][1]; }
-      wv[0] = wn[0]; wv[1] = wn[1];
-    }
-  }
-  // ---- CTA reduction in a fixed order: warp 0 stores, the other warps add one after the other ----
-  // C fragment of (I, J): c0 (row g, col 2k), c1 (g, 2k+1), c2 (g+8, 2k), c3 (g+8, 2k+1); tile slot = row * 8 + col
-  for (int wturn = 0; wturn < D16_WARPS; ++wturn) {
-    if (warp == wturn) {
-#pragma unroll
-      for (int i = 0; i < NMMA; ++i) {
-        double* d = sm + i * 128;
-        const int s0 = g * 8 + 2 * k, s1 = (g + 8) * 8 + 2 * k;
-        if (wturn == 0) { d[s0] = acc[i][0]; d[s0 + 1] = acc[i][1]; d[s1] = acc[i][2]; d[s1 + 1] = acc[i][3]; }
-        else { d[s0] += acc[i][0]; d[s0 + 1] += acc[i][1]; d[s1] += acc[i][2]; d[s1 + 1] += acc[i][3]; }
-      }
-    }
-    __syncthreads();
-  }
-  // ---- this CTA's partial, full symmetric q1 x q1 ----
-  double* out = partials + (size_t)blockIdx.x * q1 * q1;
-  for (int e = threadIdx.x; e < NMMA * 128; e += D16_WARPS * 32) {
-    const int blk = e >> 7, rr = (e >> 3) & 15, cc = e & 7;
-    int i = 0, rem = blk;
-    while (rem >= NB - 2 * i) { rem -= NB - 2 * i; ++i; }
-    const int j = 2 * i + rem;
-    const int a = 16 * i + rr, b = 8 * j + cc;
-    if (a < q1 && b < q1 && a <= b) {
-      const double v = sm[e];
-      out[(size_t)a * q1 + b] = v;
-      out[(size_t)b * q1 + a] = v;
-    }
-  }
-}
-
-template <int NB>
-static int launch_dmma16(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w, const double* mask,
-                         int64_t n, int p, int t, int grid, double* partials, cudaStream_t s) {
-  const size_t smem = (size_t)Dmma16<NB>::NMMA * 128 * sizeof(double);
-  auto k = gram_dmma16_kernel<NB>;
-  if (smem > 48 * 1024) PDSB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<grid, D16_WARPS * 32, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, partials);
-  PDSB_LAUNCH_OK();
-  count_launch();
-  return 0;
-}
 
 template <int NB>
 static int launch_dmma(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w, const double* mask,
@@ -662,104 +570,109 @@ static int launch_dmma_wide(const double* X, int64_t ldx, const double* Y, int64
   return 0;
 }
 
+template <int NB>
+static int launch_dmma_side(const double* X, int64_t ldx, const double* y, const double* w, const double* mask, int64_t n,
+                            int p, int grid, double* partials, cudaStream_t s) {
+  const size_t smem = (size_t)((NB * (NB + 1) / 2) * 64 + NB * 16 + 4) * sizeof(double);
+  if (w || mask) gram_dmma_side_kernel<NB, side_depth(NB, true), side_minb(NB, true), true><<<grid, 128, smem, s>>>(X, ldx, y, w, mask, n, p, partials);
+  else gram_dmma_side_kernel<NB, side_depth(NB, false), side_minb(NB, false), false><<<grid, 128, smem, s>>>(X, ldx, y, w, mask, n, p, partials);
+  PDSB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+// The last n % 8 rows of the wide / side kernels: one CTA, one thread per entry of the partial.
+__global__ void __launch_bounds__(128)
+gram_rows_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
+                 const double* __restrict__ w, const double* __restrict__ mask, int rows, int p, int t,
+                 double* __restrict__ out /* [q1*q1] */) {
+  const int q1 = p + t + 1;
+  auto at = [&](int c, int r) -> double {
+    if (c < p) return X[(int64_t)c * ldx + r];
+    if (c < p + t) return Y[(int64_t)(c - p) * ldy + r];
+    return mask ? mask[r] : 1.0;
+  };
+  for (int e = threadIdx.x; e < q1 * q1; e += blockDim.x) {
+    const int a = e / q1, b = e % q1;
+    double v = 0.0;
+    for (int r = 0; r < rows; ++r) v = fma(w ? w[r] : 1.0, at(a, r) * at(b, r), v);   // a*b first: M stays symmetric bit for bit
+    out[e] = v;
+  }
+}
+
+#define PDSB_NB_SWITCH(NBEXPR, CALL)                                                                              \
+  switch (NBEXPR) {                                                                                               \
+    case 1: rc = CALL(1); break; case 2: rc = CALL(2); break; case 3: rc = CALL(3); break; case 4: rc = CALL(4); break; \
+    case 5: rc = CALL(5); break; case 6: rc = CALL(6); break; case 7: rc = CALL(7); break; default: rc = CALL(8); break; \
+  }
+
 // 0 ok, 1 error, -1 not applicable (caller uses the DFMA kernel).  PDSB_K2A_DMMA=0 disables.
+// Kernel choice (B200, one call each, profiles/r02/k2a_f64*.txt), % of the measured HBM peak for f64 frames of
+// 2e7 x 33 / 5e7 x 9 / 3e7 x 17 / 1e7 x 63 columns:
+//   direct (4-row steps, scalar loads)            33 / 30 / 26 / 24   <- unaligned columns only
+//   wide   (8-row batches, 16-byte loads, ring)   51 / 72 / 73 / 44   <- several targets, or when side saves no block
+//   side   (wide + y, ones, weights on DFMAs)     53 / 80 / 80 /  -   <- one target and ceil(p / 8) < ceil((p + 2) / 8)
+// Round-2 variants that lost and were removed: m16n8k8 blocks (26 / 25), bulk-copy staged m8n8k4 (23 / 31), per-lane
+// cp.async ring in shared memory (38 / 57 / 44 / 38).  ncu (profiles/r02/k2a_*_ncu_metrics.csv): DMMA pipe 63 % busy,
+// DRAM 45 %, warps wait on the long scoreboard: 12 warps per SM (168 registers) is what the accumulators leave.
+// PDSB_K2A_KERNEL=8 forces the direct kernel, =1 the wide one also for a single target.
 static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w,
                             const double* mask, int64_t n, int p, int t, double* M, cudaStream_t s) {
   static const bool enabled = [] { const char* e = getenv("PDSB_K2A_DMMA"); return !(e && e[0] == '0'); }();
-  const int q1 = p + t + 1;
-  const int nb = (q1 + 7) / 8;
-  if (!enabled || nb < 1 || nb > 8 || n < 1) return -1;
-  // staged kernel for the whole 128-row tiles (needs 16-byte aligned columns), direct kernel for the rest
-  // PDSB_K2A_KERNEL: 8 (default) = m8n8k4 direct, 16 = m16n8k8 direct, 0 = bulk-copy staged m8n8k4 (+ m8n8k4 tail).
-  // Measured in one call (B200, 2e7 x 33 f64 / 5e7 x 9 f64, profiles/r02/k2a_f64.txt): m8n8k4 direct 33.4 % / 30.0 % of the
-  // HBM peak, m16n8k8 direct 26.3 % / 24.6 %, staged 22.9 % / 31.0 %.
   static const int kern = [] { const char* e = getenv("PDSB_K2A_KERNEL"); return e ? atoi(e) : 2; }();
-  const bool staged_on = kern == 0;
-  const int ncol = p + t + (w ? 1 : 0) + (mask ? 1 : 0);
+  const int q1 = p + t + 1;
+  const int nb = (q1 + 7) / 8, nbx = (p + 7) / 8;
+  if (!enabled || n < 1) return -1;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  const bool aligned = al16(X) && al16(Y) && (ldx % 2 == 0) && (ldy % 2 == 0) && (!w || al16(w)) && (!mask || al16(mask));
-  const size_t tile_bytes = (size_t)ncol * DT_RP * sizeof(double);
-  int stages = (int)std::min<size_t>(4, (200 * 1024 - 256) / tile_bytes);
-  const size_t red_bytes = (size_t)(nb * (nb + 1) / 2) * 64 * sizeof(double);
-  const bool wide = kern == 2 && aligned && n >= 8;       // whole 8-row batches; the last n % 8 rows go to the direct kernel
-  const int64_t ntiles = (staged_on && aligned && stages >= 2 && n >= 4096) ? n / DT_R : 0;
-  const int64_t n_main = wide ? n - n % 8 : ntiles * DT_R;
+  const bool aligned = kern != 8 && n >= 8 && al16(X) && al16(Y) && (ldx % 2 == 0) && (ldy % 2 == 0) && (!w || al16(w)) &&
+                       (!mask || al16(mask));
+  const bool side = aligned && kern != 1 && t == 1 && nbx >= 1 && nbx <= 8 && nbx < nb;   // only when it saves a block
+  const bool wide = aligned && !side && nb <= 8;
+  if (!side && nb > 8) return -1;
+  const int64_t n_main = (side || wide) ? n - n % 8 : 0;
   const int64_t n_tail = n - n_main;
-  int grid_main = 0, grid = 0;
-  if (wide) grid_main = (int)std::min<int64_t>(ceil_div(n_main, 32), (int64_t)sm_count() * (nb <= 2 ? 4 : (nb <= 6 ? 3 : 2)));
-  if (ntiles > 0) {
-    // one or two CTAs per SM, whatever shared memory allows
-    const size_t smem_need = std::max((size_t)stages * tile_bytes, red_bytes) + 2 * stages * sizeof(uint64_t) + 128;
-    const int per_sm = smem_need <= 100 * 1024 ? 2 : 1;
-    grid_main = (int)std::min<int64_t>(ntiles, (int64_t)sm_count() * per_sm);
-  }
-  if (n_tail > 0) {
-    if (kern == 16) grid = (int)std::min<int64_t>(ceil_div(n_tail, 8 * D16_WARPS), (int64_t)sm_count() * (nb <= 4 ? 4 : (nb <= 5 ? 3 : 2)));
-    else grid = (int)std::min<int64_t>(ceil_div(n_tail, 32), (int64_t)sm_count() * 4);
-  }
-  if (grid_main + grid < 1) grid = 1;
+  const int per_sm = side ? side_minb(nbx, w || mask) : wide_minb(nb);
+  const int grid_main = n_main ? (int)std::min<int64_t>(ceil_div(n_main, 32), (int64_t)sm_count() * per_sm) : 0;
+  int grid_tail = 0;
+  if (n_tail > 0) grid_tail = n_main ? 1 : (int)std::min<int64_t>(ceil_div(n_tail, 32), (int64_t)sm_count() * 4);
   double* partials = nullptr;
-  if (dev_alloc((void**)&partials, (size_t)(grid_main + grid) * q1 * q1 * sizeof(double), s)) return 1;
+  if (dev_alloc((void**)&partials, (size_t)(grid_main + grid_tail) * q1 * q1 * sizeof(double), s)) return 1;
   int rc = 0;
-  if (wide) {
-    switch (nb) {
-      case 1: rc = launch_dmma_wide<1>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
-      case 2: rc = launch_dmma_wide<2>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
-      case 3: rc = launch_dmma_wide<3>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
-      case 4: rc = launch_dmma_wide<4>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
-      case 5: rc = launch_dmma_wide<5>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
-      case 6: rc = launch_dmma_wide<6>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
-      case 7: rc = launch_dmma_wide<7>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
-      default: rc = launch_dmma_wide<8>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s); break;
-    }
-    if (rc) { dev_free(partials, s); return rc; }
-  } else if (grid_main > 0) {
-    const size_t smem = std::max((size_t)stages * tile_bytes, red_bytes) + 2 * stages * sizeof(uint64_t) + 128;
-#define PDSB_ST(NBV) rc = launch_dmma_staged<NBV>(X, ldx, Y, ldy, w, mask, ntiles, p, t, grid_main, stages, smem, partials, s)
-    switch (nb) {
-      case 1: PDSB_ST(1); break; case 2: PDSB_ST(2); break; case 3: PDSB_ST(3); break; case 4: PDSB_ST(4); break;
-      case 5: PDSB_ST(5); break; case 6: PDSB_ST(6); break; case 7: PDSB_ST(7); break; default: PDSB_ST(8); break;
-    }
-#undef PDSB_ST
-    if (rc) { dev_free(partials, s); return rc; }
+  if (side) {
+#define PDSB_CALL(NBV) launch_dmma_side<NBV>(X, ldx, Y, w, mask, n_main, p, grid_main, partials, s)
+    PDSB_NB_SWITCH(nbx, PDSB_CALL)
+#undef PDSB_CALL
+  } else if (wide) {
+#define PDSB_CALL(NBV) launch_dmma_wide<NBV>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s)
+    PDSB_NB_SWITCH(nb, PDSB_CALL)
+#undef PDSB_CALL
   }
-  if (grid > 0) {
+  if (rc) { dev_free(partials, s); return rc; }
+  if (grid_tail > 0) {
     const double* Xt = X + n_main; const double* Yt = Y + n_main;
     const double* wt = w ? w + n_main : nullptr; const double* mt = mask ? mask + n_main : nullptr;
     double* pt = partials + (size_t)grid_main * q1 * q1;
-    if (kern == 16) {
-      switch (nb) {
-        case 1: rc = launch_dmma16<1>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-        case 2: rc = launch_dmma16<2>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-        case 3: rc = launch_dmma16<3>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-        case 4: rc = launch_dmma16<4>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-        case 5: rc = launch_dmma16<5>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-        case 6: rc = launch_dmma16<6>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-        case 7: rc = launch_dmma16<7>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-        default: rc = launch_dmma16<8>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-      }
-    } else
-    switch (nb) {
-      case 1: rc = launch_dmma<1>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-      case 2: rc = launch_dmma<2>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-      case 3: rc = launch_dmma<3>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-      case 4: rc = launch_dmma<4>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-      case 5: rc = launch_dmma<5>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-      case 6: rc = launch_dmma<6>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-      case 7: rc = launch_dmma<7>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
-      default: rc = launch_dmma<8>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid, pt, s); break;
+    if (n_main) {
+      gram_rows_kernel<<<1, 128, 0, s>>>(Xt, ldx, Yt, ldy, wt, mt, (int)n_tail, p, t, pt);
+      cudaError_t e = cudaGetLastError();
+      count_launch();
+      if (e != cudaSuccess) { set_error("gram_rows launch failed: %s", cudaGetErrorString(e)); rc = 1; }
+    } else {
+#define PDSB_CALL(NBV) launch_dmma<NBV>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid_tail, pt, s)
+      PDSB_NB_SWITCH(nb, PDSB_CALL)
+#undef PDSB_CALL
     }
     if (rc) { dev_free(partials, s); return rc; }
   }
-  grid += grid_main;
   const int len = q1 * q1;
-  reduce_partials_kernel<<<len, 128, 0, s>>>(partials, grid, len, M);
+  reduce_partials_kernel<<<len, 128, 0, s>>>(partials, grid_main + grid_tail, len, M);
   cudaError_t e = cudaGetLastError();
   count_launch();
   dev_free(partials, s);
   if (e != cudaSuccess) { set_error("reduce_partials launch failed: %s", cudaGetErrorString(e)); return 1; }
   return 0;
 }
+#undef PDSB_NB_SWITCH
 
 template <typename T, int MAXT>
 static int launch_gram(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, const T* mask,

@@ -131,12 +131,16 @@ def test_simt_moments_weighted(dtype):
 @pytest.mark.parametrize("n,p,t,weighted,masked", [(100_000, 4, 1, False, False), (200_131, 32, 1, False, False),
                                                    (65_536, 32, 1, True, False), (70_003, 20, 2, False, True),
                                                    (40_000, 61, 2, True, True), (5_000, 7, 1, False, False),
-                                                   (4_096, 1, 1, False, False)])
-def test_f64_moments_staged_dmma(n, p, t, weighted, masked):
-    """The f64 path (the reference's default dtype): whole 128-row tiles through the bulk-copy staged DMMA kernel, the
-    tail through the direct one; against numpy float64, bit-reproducible, and equal to the direct kernel alone."""
-    import os
-
+                                                   (4_096, 1, 1, False, False), (300_007, 8, 1, False, True),
+                                                   (123_457, 9, 1, True, True), (90_001, 16, 1, False, False),
+                                                   (50_006, 33, 1, True, False), (64_000, 57, 1, False, True),
+                                                   (33_333, 64, 1, True, True), (20_000, 64, 1, False, False),
+                                                   (7, 3, 1, False, False), (15, 40, 1, True, False),
+                                                   (1_000_001, 30, 3, False, False)])
+def test_f64_moments_dmma(n, p, t, weighted, masked):
+    """The f64 path (the reference's default dtype) on the FP64 tensor cores: one target -> feature blocks on DMMA with
+    y / ones / weights as lane-local DFMAs (side kernel), several targets -> all columns in blocks (wide kernel), the
+    last n % 8 rows through gram_rows_kernel; against numpy float64, bit-reproducible, symmetric."""
     import torch
 
     from polars_ds_extension_b200 import device as dev
@@ -154,3 +158,19 @@ def test_f64_moments_staged_dmma(n, p, t, weighted, masked):
     scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
     assert np.max(np.abs(M1 - ref) / scale) < 1e-12
     assert np.array_equal(M1, M1.T)
+
+
+def test_f64_moments_unaligned_columns_take_the_direct_kernel():
+    """Columns that are not 16-byte aligned (a view that starts at an odd row) cannot use 16-byte loads: same numbers
+    from the 4-row direct kernel."""
+    import torch
+
+    from polars_ds_extension_b200 import device as dev
+
+    n, p = 50_001, 12
+    Z, X, Y, ld = _mk(torch, n + 1, p, 1, torch.float64, 99)
+    Xo, Yo = X[:, 1:], Y[:, 1:]
+    ref = _ref(Xo, Yo, n)
+    M = dev.moments(Xo, Yo, n=n).cpu().numpy()
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    assert np.max(np.abs(M - ref) / scale) < 1e-12
