@@ -19,15 +19,33 @@ namespace pdsb {
 
 namespace {
 
-constexpr int CHUNK = 8192;  // rows per (group, chunk) work item
+constexpr int CHUNK = 8192;  // rows per work item of the whole-frame caller; upper bound per (group, chunk) item
+// PDSB_K5_CHUNK: rows per (group, chunk) item of the grouped path (a group of len rows is cut into ceil(len / chunk)
+// items of EQUAL size, see item_range)
+static int64_t chunk_rows() {
+  static const int64_t v = [] { const char* e = getenv("PDSB_K5_CHUNK"); const long c = e ? atol(e) : 0; return (int64_t)(c >= 128 ? c : CHUNK); }();
+  return v;
+}
+
+// rows [r0, r1) of item `item` of group g: the group's rows are dealt EVENLY over its items (rounded up to 128 rows, one
+// trip of the register kernel).  Cutting at fixed CHUNK boundaries left a 1e4-row group as 8192 + 1808 rows, and with
+// items dealt round-robin over an even number of warps half the warps got only the long ones (56 % of the HBM peak).
+__device__ __forceinline__ void item_range(const int64_t* __restrict__ offsets, const int64_t* __restrict__ item_start, int64_t g,
+                                           int64_t item, int64_t& r0, int64_t& r1) {
+  const int64_t beg = offsets[g], end = offsets[g + 1];
+  const int64_t cnt = item_start[g + 1] - item_start[g];
+  const int64_t per = (((end - beg) + cnt - 1) / cnt + 127) & ~int64_t(127);
+  r0 = min(beg + (item - item_start[g]) * per, end);
+  r1 = min(r0 + per, end);
+}
 constexpr int GEN_ACC = 70;   // moments per lane of the generic-p kernel: (p+2)(p+3)/2 <= 2240 -> p <= 64
 
 // ---------------- pass 0: work list ----------------
-__global__ void count_items_kernel(const int64_t* __restrict__ offsets, int64_t n_groups, int64_t* __restrict__ item_start) {
+__global__ void count_items_kernel(const int64_t* __restrict__ offsets, int64_t n_groups, int64_t chunk, int64_t* __restrict__ item_start) {
   // item_start[g] = number of chunks of group g (scanned on the host side of this file by a tiny kernel below)
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * blockDim.x) {
     int64_t len = offsets[g + 1] - offsets[g];
-    item_start[g] = len > 0 ? (len + CHUNK - 1) / CHUNK : 1;
+    item_start[g] = len > 0 ? (len + chunk - 1) / chunk : 1;
   }
 }
 
@@ -73,8 +91,8 @@ group_moments_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__
     int64_t lo = 0, hi = n_groups;
     while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (item_start[mid] <= item) lo = mid; else hi = mid; }
     const int64_t g = lo;
-    const int64_t r0 = offsets[g] + (item - item_start[g]) * CHUNK;
-    const int64_t r1 = min(r0 + (int64_t)CHUNK, offsets[g + 1]);
+    int64_t r0, r1;
+    item_range(offsets, item_start, g, item, r0, r1);
     T acc[NM];
 #pragma unroll
     for (int k = 0; k < NM; ++k) acc[k] = T(0);
@@ -108,6 +126,8 @@ group_moments_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__
           for (int j = i; j < Q1; ++j) { acc[k] = fma(z[u][i], z[u][j], acc[k]); ++k; }
       }
     }
+    // (a transpose-reduce in T — NM - NM / 32 shuffles instead of 5 f64 shuffles per value — was measured twice in round 2:
+    // ptxas then keeps fewer of the U x (P + 1) loads in flight and the kernel drops from 4.2 to 2.5 TB/s)
 #pragma unroll
     for (int k = 0; k < NM; ++k) {
       double v = (double)acc[k];
@@ -169,8 +189,8 @@ group_moments_vec_kernel(const T* __restrict__ X, int64_t ldx, const T* __restri
     int64_t lo = 0, hi = n_groups;
     while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (item_start[mid] <= item) lo = mid; else hi = mid; }
     const int64_t g = lo;
-    const int64_t r0 = offsets[g] + (item - item_start[g]) * CHUNK;
-    const int64_t r1 = min(r0 + (int64_t)CHUNK, offsets[g + 1]);
+    int64_t r0, r1;
+    item_range(offsets, item_start, g, item, r0, r1);
     T acc[NM];
 #pragma unroll
     for (int k = 0; k < NM; ++k) acc[k] = T(0);
@@ -249,9 +269,10 @@ __global__ void item_rows_kernel(const int64_t* __restrict__ offsets, const int6
   for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (int64_t)gridDim.x * blockDim.x) {
     int64_t lo = 0, hi = n_groups;
     while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (item_start[mid] <= item) lo = mid; else hi = mid; }
-    const int64_t r0 = offsets[lo] + (item - item_start[lo]) * CHUNK;
+    int64_t r0, r1;
+    item_range(offsets, item_start, lo, item, r0, r1);
     rows[2 * item] = r0;
-    rows[2 * item + 1] = min(r0 + (int64_t)CHUNK, offsets[lo + 1]);
+    rows[2 * item + 1] = r1;
   }
 }
 
@@ -419,8 +440,8 @@ group_moments_generic_kernel(const T* __restrict__ X, int64_t ldx, const T* __re
     int64_t lo = 0, hi = n_groups;
     while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (item_start[mid] <= item) lo = mid; else hi = mid; }
     const int64_t g = lo;
-    const int64_t r0 = offsets[g] + (item - item_start[g]) * CHUNK;
-    const int64_t r1 = min(r0 + (int64_t)CHUNK, offsets[g + 1]);
+    int64_t r0, r1;
+    item_range(offsets, item_start, g, item, r0, r1);
     double acc[GEN_ACC];   // supports nm <= 32 * GEN_ACC (p <= 64)
     for (int k = 0; k < GEN_ACC; ++k) acc[k] = 0.0;
     for (int64_t rb = r0; rb < r1; rb += 32) {
@@ -753,7 +774,7 @@ int grouped_lin_reg(const T* X, int64_t ldx, const T* y, const int64_t* offsets,
   // work list: we need n_items on the host to size the partial buffer -> one small D2H
   int64_t* item_start = nullptr;
   if (dev_alloc((void**)&item_start, (size_t)(n_groups + 1) * sizeof(int64_t), s)) return 1;
-  count_items_kernel<<<(int)std::min<int64_t>(ceil_div(n_groups, 256), 1024), 256, 0, s>>>(offsets, n_groups, item_start);
+  count_items_kernel<<<(int)std::min<int64_t>(ceil_div(n_groups, 256), 1024), 256, 0, s>>>(offsets, n_groups, chunk_rows(), item_start);
   count_launch();
   scan_items_kernel<<<1, 1024, 0, s>>>(item_start, n_groups);
   count_launch();
