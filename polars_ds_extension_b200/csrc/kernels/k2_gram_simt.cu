@@ -539,43 +539,68 @@ gram_dmma_side_kernel(const double* __restrict__ X, int64_t ldx, const double* _
   }
 }
 
-// ring depth and CTAs per SM (128 threads each) by block count: what fits 65536 registers without spilling in the loop
-constexpr int side_depth(int nb, bool aux) { return aux ? (nb <= 1 ? 5 : (nb <= 2 ? 4 : (nb <= 3 ? 3 : 2))) : (nb <= 1 ? 8 : (nb <= 2 ? 5 : (nb <= 4 ? 3 : 2))); }
-constexpr int side_minb(int nb, bool aux) { return aux ? (nb <= 2 ? 4 : (nb <= 4 ? 3 : 2)) : (nb <= 2 ? 4 : (nb <= 5 ? 3 : 2)); }
-constexpr int wide_minb(int nb) { return nb <= 2 ? 4 : (nb <= 6 ? 3 : 2); }
+// Ring depth per (kernel, AUX, NB): measured, not derived (profiles/r02/k2a_depth_sweep.txt, sweep build with every depth
+// 2..9 instantiated under __launch_bounds__(128, 2), the number of resident CTAs following from the registers ptxas used).
+// Two things decide: a spill inside the loop is expensive (p = 32: depth 4 with 234 registers and no spill 73 % of the
+// HBM peak, depth 5 with a 16-byte spill 59 %), and for one or two blocks a shallow ring with more resident CTAs beats
+// a deep one (p = 8: depth 2 93 %, depth 8 68 %).
+constexpr int side_depth(int nb, bool aux) {
+  constexpr int plain[8] = {2, 8, 6, 4, 3, 3, 2, 3}, auxd[8] = {2, 7, 5, 5, 2, 3, 2, 2};
+  return aux ? auxd[nb - 1] : plain[nb - 1];
+}
+constexpr int wide_depth(int nb, bool aux) {
+  constexpr int plain[8] = {2, 9, 2, 7, 4, 4, 3, 2}, auxd[8] = {7, 3, 9, 6, 5, 3, 3, 2};
+  return aux ? auxd[nb - 1] : plain[nb - 1];
+}
 
-template <int NB> struct WideCfg {
-  static constexpr int DEPTH = NB <= 2 ? 6 : (NB <= 4 ? 4 : (NB == 5 ? 3 : 2));
-  static constexpr int MINB = wide_minb(NB);
-};
+using SideFn = void (*)(const double*, int64_t, const double*, const double*, const double*, int64_t, int, double*);
+using WideFn = void (*)(const double*, int64_t, const double*, int64_t, const double*, const double*, int64_t, int, int, double*);
+
+#ifdef PDSB_K2A_SWEEP   // sweep build (profiles/_ab): every depth 2..9 is instantiated, PDSB_K2A_DEPTH picks one per call
+static int k2a_sweep_depth() { const char* e = getenv("PDSB_K2A_DEPTH"); return e ? atoi(e) : 0; }
+#define PDSB_DEPTH_CASES(KERNEL, NBV, AUXV)                                                                          \
+  switch (k2a_sweep_depth()) {                                                                                       \
+    case 2: return KERNEL<NBV, 2, 2, AUXV>; case 3: return KERNEL<NBV, 3, 2, AUXV>; case 4: return KERNEL<NBV, 4, 2, AUXV>; \
+    case 5: return KERNEL<NBV, 5, 2, AUXV>; case 6: return KERNEL<NBV, 6, 2, AUXV>; case 7: return KERNEL<NBV, 7, 2, AUXV>; \
+    case 8: return KERNEL<NBV, 8, 2, AUXV>; case 9: return KERNEL<NBV, 9, 2, AUXV>; default: break;                  \
+  }
+#else
+#define PDSB_DEPTH_CASES(KERNEL, NBV, AUXV)
+#endif
+
+template <int NB, bool AUX> static SideFn side_fn() {
+  PDSB_DEPTH_CASES(gram_dmma_side_kernel, NB, AUX)
+  return gram_dmma_side_kernel<NB, side_depth(NB, AUX), 2, AUX>;
+}
+template <int NB, bool AUX> static WideFn wide_fn() {
+  PDSB_DEPTH_CASES(gram_dmma_wide_kernel, NB, AUX)
+  return gram_dmma_wide_kernel<NB, wide_depth(NB, AUX), 2, AUX>;
+}
+static SideFn side_fn_rt(int nb, bool aux) {
+  switch (nb) {
+    case 1: return aux ? side_fn<1, true>() : side_fn<1, false>(); case 2: return aux ? side_fn<2, true>() : side_fn<2, false>();
+    case 3: return aux ? side_fn<3, true>() : side_fn<3, false>(); case 4: return aux ? side_fn<4, true>() : side_fn<4, false>();
+    case 5: return aux ? side_fn<5, true>() : side_fn<5, false>(); case 6: return aux ? side_fn<6, true>() : side_fn<6, false>();
+    case 7: return aux ? side_fn<7, true>() : side_fn<7, false>(); default: return aux ? side_fn<8, true>() : side_fn<8, false>();
+  }
+}
+static WideFn wide_fn_rt(int nb, bool aux) {
+  switch (nb) {
+    case 1: return aux ? wide_fn<1, true>() : wide_fn<1, false>(); case 2: return aux ? wide_fn<2, true>() : wide_fn<2, false>();
+    case 3: return aux ? wide_fn<3, true>() : wide_fn<3, false>(); case 4: return aux ? wide_fn<4, true>() : wide_fn<4, false>();
+    case 5: return aux ? wide_fn<5, true>() : wide_fn<5, false>(); case 6: return aux ? wide_fn<6, true>() : wide_fn<6, false>();
+    case 7: return aux ? wide_fn<7, true>() : wide_fn<7, false>(); default: return aux ? wide_fn<8, true>() : wide_fn<8, false>();
+  }
+}
+#undef PDSB_DEPTH_CASES
+// shared memory of the CTA-level reduction (both kernels): [NP][64] blocks + [NB * 8][2] side sums + scalars
+static size_t ring_kernel_smem(int nb) { return (size_t)((nb * (nb + 1) / 2) * 64 + nb * 16 + 4) * sizeof(double); }
 
 template <int NB>
 static int launch_dmma(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w, const double* mask,
                        int64_t n, int p, int t, int grid, double* partials, cudaStream_t s) {
   const size_t smem = (size_t)(NB * (NB + 1) / 2) * 64 * sizeof(double);
   gram_dmma_kernel<NB><<<grid, 256, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, partials);
-  PDSB_LAUNCH_OK();
-  count_launch();
-  return 0;
-}
-
-template <int NB>
-static int launch_dmma_wide(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w, const double* mask,
-                            int64_t n, int p, int t, int grid, double* partials, cudaStream_t s) {
-  const size_t smem = (size_t)(NB * (NB + 1) / 2) * 64 * sizeof(double);
-  if (w) gram_dmma_wide_kernel<NB, WideCfg<NB>::DEPTH, WideCfg<NB>::MINB, true><<<grid, 128, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, partials);
-  else gram_dmma_wide_kernel<NB, WideCfg<NB>::DEPTH, WideCfg<NB>::MINB, false><<<grid, 128, smem, s>>>(X, ldx, Y, ldy, w, mask, n, p, t, partials);
-  PDSB_LAUNCH_OK();
-  count_launch();
-  return 0;
-}
-
-template <int NB>
-static int launch_dmma_side(const double* X, int64_t ldx, const double* y, const double* w, const double* mask, int64_t n,
-                            int p, int grid, double* partials, cudaStream_t s) {
-  const size_t smem = (size_t)((NB * (NB + 1) / 2) * 64 + NB * 16 + 4) * sizeof(double);
-  if (w || mask) gram_dmma_side_kernel<NB, side_depth(NB, true), side_minb(NB, true), true><<<grid, 128, smem, s>>>(X, ldx, y, w, mask, n, p, partials);
-  else gram_dmma_side_kernel<NB, side_depth(NB, false), side_minb(NB, false), false><<<grid, 128, smem, s>>>(X, ldx, y, w, mask, n, p, partials);
   PDSB_LAUNCH_OK();
   count_launch();
   return 0;
@@ -607,14 +632,15 @@ gram_rows_kernel(const double* __restrict__ X, int64_t ldx, const double* __rest
   }
 
 // 0 ok, 1 error, -1 not applicable (caller uses the DFMA kernel).  PDSB_K2A_DMMA=0 disables.
-// Kernel choice (B200, one call each, profiles/r02/k2a_f64*.txt), % of the measured HBM peak for f64 frames of
-// 2e7 x 33 / 5e7 x 9 / 3e7 x 17 / 1e7 x 63 columns:
-//   direct (4-row steps, scalar loads)            33 / 30 / 26 / 24   <- unaligned columns only
-//   wide   (8-row batches, 16-byte loads, ring)   51 / 72 / 73 / 44   <- several targets, or when side saves no block
-//   side   (wide + y, ones, weights on DFMAs)     53 / 80 / 80 /  -   <- one target and ceil(p / 8) < ceil((p + 2) / 8)
-// Round-2 variants that lost and were removed: m16n8k8 blocks (26 / 25), bulk-copy staged m8n8k4 (23 / 31), per-lane
-// cp.async ring in shared memory (38 / 57 / 44 / 38).  ncu (profiles/r02/k2a_*_ncu_metrics.csv): DMMA pipe 63 % busy,
-// DRAM 45 %, warps wait on the long scoreboard: 12 warps per SM (168 registers) is what the accumulators leave.
+// Kernel choice (B200, profiles/r02/k2a_f64*.txt and k2a_depth_sweep.txt), % of the measured HBM peak for f64 frames with
+// 8 / 16 / 24 / 32 / 48 / 62 features and one target:
+//   direct (4-row steps, scalar loads)            30 / 26 /  - / 33 /  - / 24   <- unaligned columns only
+//   wide   (8-row batches, 16-byte loads, ring)   several targets, or when side saves no block: 14 features 92, 30: 67, 62: 44
+//   side   (wide + y, ones, weights on DFMAs)     93 / 79 / 78 / 73 / 52 /  -   <- one target and ceil(p / 8) < ceil((p + 2) / 8)
+// (p = 63, 64: 21 %, the 8-block side kernel spills; the SIMT fallback measured 11 %.)
+// Round-2 variants that lost and were removed: m16n8k8 blocks (26 % at 32 features), bulk-copy staged m8n8k4 (23 %), per-lane
+// cp.async ring in shared memory (38 %).  ncu (profiles/r02/k2a_*_ncu_metrics.csv, before the depth sweep): DMMA pipe 54-63 %
+// busy, DRAM 42-45 %, warps wait on the long scoreboard.
 // PDSB_K2A_KERNEL=8 forces the direct kernel, =1 the wide one also for a single target.
 static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w,
                             const double* mask, int64_t n, int p, int t, double* M, cudaStream_t s) {
@@ -631,7 +657,17 @@ static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64
   if (!side && nb > 8) return -1;
   const int64_t n_main = (side || wide) ? n - n % 8 : 0;
   const int64_t n_tail = n - n_main;
-  const int per_sm = side ? side_minb(nbx, w || mask) : wide_minb(nb);
+  // resident CTAs of the chosen instantiation (128 threads): from the registers ptxas used for it
+  SideFn sfn = nullptr; WideFn wfn = nullptr;
+  int per_sm = 4;
+  const size_t ring_smem = ring_kernel_smem(side ? nbx : nb);
+  if (side) {
+    sfn = side_fn_rt(nbx, w || mask);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sfn, 128, ring_smem) != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 2; }
+  } else if (wide) {
+    wfn = wide_fn_rt(nb, w != nullptr);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wfn, 128, ring_smem) != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 2; }
+  }
   const int grid_main = n_main ? (int)std::min<int64_t>(ceil_div(n_main, 32), (int64_t)sm_count() * per_sm) : 0;
   int grid_tail = 0;
   if (n_tail > 0) grid_tail = n_main ? 1 : (int)std::min<int64_t>(ceil_div(n_tail, 32), (int64_t)sm_count() * 4);
@@ -639,13 +675,15 @@ static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64
   if (dev_alloc((void**)&partials, (size_t)(grid_main + grid_tail) * q1 * q1 * sizeof(double), s)) return 1;
   int rc = 0;
   if (side) {
-#define PDSB_CALL(NBV) launch_dmma_side<NBV>(X, ldx, Y, w, mask, n_main, p, grid_main, partials, s)
-    PDSB_NB_SWITCH(nbx, PDSB_CALL)
-#undef PDSB_CALL
+    sfn<<<grid_main, 128, ring_smem, s>>>(X, ldx, Y, w, mask, n_main, p, partials);
+    cudaError_t e = cudaGetLastError();
+    count_launch();
+    if (e != cudaSuccess) { set_error("gram_dmma_side launch failed: %s", cudaGetErrorString(e)); rc = 1; }
   } else if (wide) {
-#define PDSB_CALL(NBV) launch_dmma_wide<NBV>(X, ldx, Y, ldy, w, mask, n_main, p, t, grid_main, partials, s)
-    PDSB_NB_SWITCH(nb, PDSB_CALL)
-#undef PDSB_CALL
+    wfn<<<grid_main, 128, ring_smem, s>>>(X, ldx, Y, ldy, w, mask, n_main, p, t, partials);
+    cudaError_t e = cudaGetLastError();
+    count_launch();
+    if (e != cudaSuccess) { set_error("gram_dmma_wide launch failed: %s", cudaGetErrorString(e)); rc = 1; }
   }
   if (rc) { dev_free(partials, s); return rc; }
   if (grid_tail > 0) {
