@@ -76,23 +76,40 @@ __global__ void scan_items_kernel(int64_t* __restrict__ item_start, int64_t n_gr
 // Z = [x_0 .. x_{P-1}, y, 1];  Q1 = P + 2 columns; NM = Q1 (Q1+1) / 2 packed upper-triangular moments.
 // SKIP_NAN: null rows arrive as NaN and drop out of their group (the grouped path).  The whole-frame caller (moments_small)
 // passes false: there a NaN must poison the moments exactly like in the other moments kernels.
-template <typename T, int P, bool SKIP_NAN = true>
+// MODE bit 0: the item's rows come from a precomputed [n_items][2] array (item_rows_kernel) instead of a 14-step binary
+// search in front of every item; bit 1: warps take items from a global counter (persistent grid) instead of a fixed
+// stride, so a warp with a short item does not idle while its CTA's longest one finishes.
+template <typename T, int P, bool SKIP_NAN = true, int MODE = 0>
 __global__ void __launch_bounds__(256)
 group_moments_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y,
                      const int64_t* __restrict__ offsets, const int64_t* __restrict__ item_start,
-                     int64_t n_groups, int64_t n_items, double* __restrict__ part /* [NM][n_items] */) {
+                     int64_t n_groups, int64_t n_items, double* __restrict__ part /* [NM][n_items] */,
+                     const int64_t* __restrict__ rows = nullptr, unsigned long long* __restrict__ queue = nullptr) {
   constexpr int Q1 = P + 2;
   constexpr int NM = Q1 * (Q1 + 1) / 2;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t item = warp_global; item < n_items; item += nwarps) {
-    // binary search the group of this item: item_start[g] <= item < item_start[g+1]
-    int64_t lo = 0, hi = n_groups;
-    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (item_start[mid] <= item) lo = mid; else hi = mid; }
-    const int64_t g = lo;
+  auto next_item = [&](int64_t cur) -> int64_t {
+    if constexpr ((MODE & 2) != 0) {
+      unsigned long long v = 0;
+      if (lane == 0) v = atomicAdd(queue, 1ULL);
+      return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+    } else {
+      return cur + nwarps;
+    }
+  };
+  for (int64_t item = (MODE & 2) ? next_item(0) : warp_global; item < n_items; item = next_item(item)) {
     int64_t r0, r1;
-    item_range(offsets, item_start, g, item, r0, r1);
+    if constexpr ((MODE & 1) != 0) {
+      r0 = rows[2 * item];
+      r1 = rows[2 * item + 1];
+    } else {
+      // binary search the group of this item: item_start[g] <= item < item_start[g+1]
+      int64_t lo = 0, hi = n_groups;
+      while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (item_start[mid] <= item) lo = mid; else hi = mid; }
+      item_range(offsets, item_start, lo, item, r0, r1);
+    }
     T acc[NM];
 #pragma unroll
     for (int k = 0; k < NM; ++k) acc[k] = T(0);
@@ -480,7 +497,7 @@ struct GroupSolveArgs {
   const double* part; const int64_t* item_start; const int64_t* offsets;
   int64_t n_groups, n_items; int p, add_bias, solver; double l2, tol;
   int method, positive, max_iter; double l1, cd_tol;      // PDSB_METHOD_CD / _NNLS per group (lr_solvers.rs:426-600)
-  double* ws;      // [(q*q + 2q) ][n_groups]  interleaved
+  double* ws;      // [(q*q + 2q) ][n_groups]  interleaved; nullptr: the workspace lives in shared memory, [(q*q + 2q)][blockDim.x]
   double* beta;    // [n_groups][q]
   int* status;
 };
@@ -489,10 +506,15 @@ __global__ void __launch_bounds__(128) group_solve_kernel(GroupSolveArgs a) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= a.n_groups) return;
   const int p = a.p, q = p + (a.add_bias ? 1 : 0), q1 = p + 2;
-  const int64_t NG = a.n_groups;
-  double* A = a.ws + g;                                  // A(i,j) = A[(i + j*q) * NG]
-  double* b = a.ws + (size_t)q * q * NG + g;             // b(i)   = b[i * NG]
-  double* cn = a.ws + ((size_t)q * q + q) * NG + g;      // scratch q
+  // one thread per group walks dependent chains over its q x q system: in global memory every step pays a DRAM / L2 round
+  // trip (0.113 ms for 1e4 groups of 9 coefficients, 14 % of the C3 step); up to ~20 coefficients the workspace of a
+  // 32-thread CTA fits shared memory instead (same interleaved layout, stride = threads per CTA)
+  extern __shared__ double gs_smem[];
+  const int64_t NG = a.ws ? a.n_groups : (int64_t)blockDim.x;
+  double* base = a.ws ? a.ws + g : gs_smem + threadIdx.x;
+  double* A = base;                                      // A(i,j) = A[(i + j*q) * NG]
+  double* b = base + (size_t)q * q * NG;                 // b(i)   = b[i * NG]
+  double* cn = base + ((size_t)q * q + q) * NG;          // scratch q
 #define AA(i, j) A[((size_t)(i) + (size_t)(j) * q) * NG]
 #define BB(i) b[(size_t)(i) * NG]
 #define CN(i) cn[(size_t)(i) * NG]
@@ -500,7 +522,38 @@ __global__ void __launch_bounds__(128) group_solve_kernel(GroupSolveArgs a) {
   auto midx = [&](int i, int j) { if (i > j) { int t = i; i = j; j = t; } return i * q1 - i * (i - 1) / 2 + (j - i); };
   auto fz = [&](int i) { return i < p ? i : p + 1; };    // coefficient index -> Z column (bias -> ones)
   const int64_t it0 = a.item_start[g], it1 = a.item_start[g + 1];
-  auto mom = [&](int k) { double s = 0.0; for (int64_t it = it0; it < it1; ++it) s += a.part[(size_t)k * a.n_items + it]; return s; };
+  const double* __restrict__ part = a.part;
+  const int nm = q1 * (q1 + 1) / 2;
+  // the group's moments, summed over its items in a fixed order.  With the shared-memory workspace they are gathered
+  // first, eight independent loads at a time (a load followed at once by its consumer serialises on the in-order issue:
+  // 64 dependent round trips were 40 of the kernel's 97 microseconds at 9 coefficients)
+  double* ms = a.ws ? nullptr : base + ((size_t)q * q + 2 * q) * NG;     // ms(k) = ms[k * NG]
+  if (ms) {
+    for (int k0 = 0; k0 < nm; k0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u < nm ? k0 + u : nm - 1;
+        v[u] = part[(size_t)k * a.n_items + it0];
+      }
+      for (int64_t it = it0 + 1; it < it1; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = k0 + u < nm ? k0 + u : nm - 1;
+          v[u] += part[(size_t)k * a.n_items + it];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (k0 + u < nm) ms[(size_t)(k0 + u) * NG] = v[u];
+    }
+  }
+  auto mom = [&](int k) {
+    if (ms) return ms[(size_t)k * NG];
+    double s = 0.0;
+    for (int64_t it = it0; it < it1; ++it) s += part[(size_t)k * a.n_items + it];
+    return s;
+  };
   const int64_t nrows = (int64_t)llround(mom(midx(p + 1, p + 1)));   // valid rows of the group
   double* out = a.beta + (size_t)g * q;
   if (nrows < q) {  // "#Data < #features" would be an error for a single call; per group it yields null
@@ -710,8 +763,40 @@ int launch_moments_p(const T* X, int64_t ldx, const T* y, const int64_t* offsets
   if (launched) {
   } else if (vec_on && aligned && P <= 10)
     group_moments_vec_kernel<T, P><<<grid, 256, 0, s>>>(X, ldx, y, offsets, item_start, n_groups, n_items, n, part);
-  else
-    group_moments_kernel<T, P><<<grid, 256, 0, s>>>(X, ldx, y, offsets, item_start, n_groups, n_items, part);
+  else {
+    // PDSB_K5_MODE: 0 = binary search + fixed stride (round 1), 1 = precomputed rows, 2 = work queue, 3 = both (default;
+    // C3 in one call: 0.861 / 0.852 / 0.810 / 0.805 ms, profiles/r02/k5_mode_sweep.txt)
+    static const int mode = [] { const char* e = getenv("PDSB_K5_MODE"); return e ? atoi(e) : 3; }();
+    int64_t* rows = nullptr;
+    unsigned long long* queue = nullptr;
+    if (mode & 1) {
+      if (dev_alloc((void**)&rows, (size_t)n_items * 2 * sizeof(int64_t), s)) return 1;
+      item_rows_kernel<<<(int)std::min<int64_t>(ceil_div(n_items, 256), 2048), 256, 0, s>>>(offsets, item_start, n_groups, n_items, rows);
+      count_launch();
+    }
+    if (mode & 2) {
+      if (dev_alloc((void**)&queue, sizeof(unsigned long long), s)) return 1;
+      PDSB_CUDA_OK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
+    }
+    auto launch = [&](auto kern) {
+      int g = grid;
+      if (mode & 2) {      // persistent: exactly the resident CTAs
+        int occ = 2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ < 1) { (void)cudaGetLastError(); occ = 2; }
+        g = (int)std::min<int64_t>(ceil_div(n_items, (int64_t)8), (int64_t)sm_count() * occ);
+        if (g < 1) g = 1;
+      }
+      kern<<<g, 256, 0, s>>>(X, ldx, y, offsets, item_start, n_groups, n_items, part, rows, queue);
+    };
+    switch (mode & 3) {
+      case 1: launch(group_moments_kernel<T, P, true, 1>); break;
+      case 2: launch(group_moments_kernel<T, P, true, 2>); break;
+      case 3: launch(group_moments_kernel<T, P, true, 3>); break;
+      default: launch(group_moments_kernel<T, P, true, 0>); break;
+    }
+    if (rows) dev_free(rows, s);
+    if (queue) dev_free(queue, s);
+  }
   PDSB_LAUNCH_OK();
   count_launch();
   return 0;
@@ -799,14 +884,22 @@ int grouped_lin_reg(const T* X, int64_t ldx, const T* y, const int64_t* offsets,
   }
 #undef CASE_P
   double* ws = nullptr;
-  if (!rc && dev_alloc((void**)&ws, ((size_t)q * q + 2 * q) * n_groups * sizeof(double), s)) rc = 1;
+  const size_t ws_per_thread = ((size_t)q * q + 2 * q + (size_t)(p + 2) * (p + 3) / 2) * sizeof(double);   // A, b, scratch, moments
+  const bool ws_shared = ws_per_thread * 32 <= (size_t)200 * 1024;
+  if (!rc && !ws_shared && dev_alloc((void**)&ws, ((size_t)q * q + 2 * q) * sizeof(double) * n_groups, s)) rc = 1;
   if (!rc) {
     GroupSolveArgs a;
     a.part = part; a.item_start = item_start; a.offsets = offsets; a.n_groups = n_groups; a.n_items = n_items;
     a.p = p; a.add_bias = o.add_bias; a.solver = o.solver; a.l2 = o.l2_reg; a.tol = o.singular_x_tol;
     a.method = o.method; a.positive = o.positive; a.max_iter = o.max_iter; a.l1 = o.l1_reg; a.cd_tol = o.tol;
     a.ws = ws; a.beta = beta; a.status = status;
-    group_solve_kernel<<<(int)ceil_div(n_groups, 128), 128, 0, s>>>(a);
+    if (ws_shared) {
+      const size_t smem = ws_per_thread * 32;
+      if (smem > 48 * 1024) PDSB_CUDA_OK(cudaFuncSetAttribute(group_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      group_solve_kernel<<<(int)ceil_div(n_groups, 32), 32, smem, s>>>(a);
+    } else {
+      group_solve_kernel<<<(int)ceil_div(n_groups, 128), 128, 0, s>>>(a);
+    }
     cudaError_t e = cudaGetLastError();
     count_launch();
     if (e != cudaSuccess) { set_error("group solve launch failed: %s", cudaGetErrorString(e)); rc = 1; }
