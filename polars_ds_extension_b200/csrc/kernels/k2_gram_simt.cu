@@ -261,6 +261,15 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, const double* __rest
   }
 }
 
+// two consecutive rows of a column as they sit in memory (the ring holds them RAW: a conversion right behind the load would
+// make the warp wait for it) and as the DMMA wants them
+template <typename T> struct Rows2;
+template <> struct Rows2<double> { using V = double2; };
+template <> struct Rows2<float> { using V = float2; };
+__device__ __forceinline__ double2 rows2_f64(const double2& v) { return v; }
+__device__ __forceinline__ double2 rows2_f64(const float2& v) { return make_double2((double)v.x, (double)v.y); }
+template <typename V> __device__ __forceinline__ V rows2_fill(float a) { V v; v.x = a; v.y = a; return v; }
+
 // ------------------------------------------------------------------------------------------------------------
 // Wide variant: the direct kernel keeps 4 rows x (p + t) x 8 B in flight per warp and measured 33 % of the HBM peak with
 // the DMMA pipe at 43 % of ITS measured peak (profiles/fp64_peak.cu: 37 TFLOP/s for every mma.sync f64 shape, 33 for
@@ -270,18 +279,21 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, const double* __rest
 // next.  DEPTH batches live in a register ring (the loop is unrolled over the ring, so every index is static): DEPTH - 1
 // batches = 8 (DEPTH - 1) rows per warp are in flight while one is multiplied.  The mask is just the "ones" column read
 // from memory.  128-thread CTAs, MINB per SM.  Needs 16-byte aligned columns and even leading dimensions.
-template <int NB, int DEPTH, int MINB, bool WEIGHTED>
+// T = float: the same kernel for f32 columns (8-byte loads, converted when multiplied): weighted / many-target f32 fits
+// that the tcgen05 kernel does not take get exact f64 products and sums at the DMMA rate instead of the SIMT kernel's 15 %.
+template <typename T, int NB, int DEPTH, int MINB, bool WEIGHTED>
 __global__ void __launch_bounds__(128, MINB)
-gram_dmma_wide_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
-                      const double* __restrict__ w, const double* __restrict__ mask, int64_t n, int p, int t,
+gram_dmma_wide_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ Y, int64_t ldy,
+                      const T* __restrict__ w, const T* __restrict__ mask, int64_t n, int p, int t,
                       double* __restrict__ partials /* [grid][q1*q1] */) {
+  using V = typename Rows2<T>::V;
   constexpr int NP = NB * (NB + 1) / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);      // [NP][64]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, k = lane & 3;
   const int q1 = p + t + 1;
-  const double* colp[NB];
+  const T* colp[NB];
   int kind[NB];                                           // 0 load, 1 ones, 2 zero padding
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
@@ -293,34 +305,39 @@ gram_dmma_wide_kernel(const double* __restrict__ X, int64_t ldx, const double* _
 #pragma unroll
   for (int i = 0; i < NP; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
 
-  double2 buf[DEPTH][NB];
-  double2 wb[DEPTH];
+  V buf[DEPTH][NB];
+  V wb[DEPTH];
   const int64_t S = (int64_t)gridDim.x * 4 * 8;
   const int64_t r0 = ((int64_t)blockIdx.x * 4 + warp) * 8;
   int64_t rl = r0 + 2 * k;                                // this lane's first row of the NEXT batch to load
-  const double* wp = WEIGHTED ? w + rl : nullptr;
+  const T* wp = WEIGHTED ? w + rl : nullptr;
 #pragma unroll
   for (int b = 0; b < NB; ++b) colp[b] += rl;
-  auto load_batch = [&](double2* z, double2& wv) {        // n is a multiple of 8 here: a batch is all in or all out
+  auto load_batch = [&](V* z, V& wv) {                    // n is a multiple of 8 here: a batch is all in or all out
     const bool in = rl < n;
     if constexpr (WEIGHTED) {
-      wv = make_double2(0.0, 0.0);
-      if (in) wv = __ldcs(reinterpret_cast<const double2*>(wp));
+      wv = rows2_fill<V>(0.0f);
+      if (in) wv = __ldcs(reinterpret_cast<const V*>(wp));
       wp += S;
     }
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-      double2 v = make_double2(0.0, 0.0);
+      V v = rows2_fill<V>(0.0f);
       if (in) {
-        if (kind[b] == 0) v = __ldcs(reinterpret_cast<const double2*>(colp[b]));
-        else if (kind[b] == 1) v = make_double2(1.0, 1.0);
+        if (kind[b] == 0) v = __ldcs(reinterpret_cast<const V*>(colp[b]));
+        else if (kind[b] == 1) v = rows2_fill<V>(1.0f);
       }
       z[b] = v;
       colp[b] += S;
     }
     rl += S;
   };
-  auto multiply = [&](const double2* z, const double2& wv) {
+  auto multiply = [&](const V* zr, const V& wr) {
+    double2 z[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) z[b] = rows2_f64(zr[b]);
+    double2 wv = make_double2(1.0, 1.0);
+    if constexpr (WEIGHTED) wv = rows2_f64(wr);
     // all block pairs for the even rows, then all for the odd rows: consecutive DMMAs never share an accumulator
     int idx = 0;
 #pragma unroll
@@ -380,11 +397,12 @@ gram_dmma_wide_kernel(const double* __restrict__ X, int64_t ldx, const double* _
 // the same 16 bytes).  p = 32 needs 10 block pairs instead of the 15 that [X | y | 1] = 34 -> 40 columns cost, p = 8 one
 // instead of 3: the DMMA pipe (37 TFLOP/s measured) is the bound of this path, so the padding columns were the waste.
 // AUX = weights and / or mask present (a missing one is loaded as ones).
-template <int NB, int DEPTH, int MINB, bool AUX>
+template <typename T, int NB, int DEPTH, int MINB, bool AUX>
 __global__ void __launch_bounds__(128, MINB)
-gram_dmma_side_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ y,
-                      const double* __restrict__ w, const double* __restrict__ mask, int64_t n, int p,
+gram_dmma_side_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y,
+                      const T* __restrict__ w, const T* __restrict__ mask, int64_t n, int p,
                       double* __restrict__ partials /* [grid][(p+2)^2] */) {
+  using V = typename Rows2<T>::V;
   constexpr int NP = NB * (NB + 1) / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);      // [NP][64] blocks, then [NB * 8][2] (x.y, sum x), then 3 scalars
@@ -393,7 +411,7 @@ gram_dmma_side_kernel(const double* __restrict__ X, int64_t ldx, const double* _
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, k = lane & 3;
   const int q1 = p + 2;
-  const double* colp[NB];
+  const T* colp[NB];
   bool live[NB];
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
@@ -408,24 +426,24 @@ gram_dmma_side_kernel(const double* __restrict__ X, int64_t ldx, const double* _
 #pragma unroll
   for (int b = 0; b < NB; ++b) { xy[b] = 0.0; x1[b] = 0.0; }
 
-  struct Batch { double2 z[NB]; double2 y, w, m; };
+  struct Batch { V z[NB]; V y, w, m; };
   Batch ring[DEPTH];
   const int64_t S = (int64_t)gridDim.x * 4 * 8;
   const int64_t r0 = ((int64_t)blockIdx.x * 4 + warp) * 8;
   int64_t rl = r0 + 2 * k;
-  const double* yp = y + rl;
-  const double* wp = (AUX && w) ? w + rl : nullptr;
-  const double* mp = (AUX && mask) ? mask + rl : nullptr;
+  const T* yp = y + rl;
+  const T* wp = (AUX && w) ? w + rl : nullptr;
+  const T* mp = (AUX && mask) ? mask + rl : nullptr;
 #pragma unroll
   for (int b = 0; b < NB; ++b) colp[b] += rl;
   auto load_batch = [&](Batch& q) {                       // n is a multiple of 8 here: a batch is all in or all out
     const bool in = rl < n;
-    const double2 zero = make_double2(0.0, 0.0), one = make_double2(1.0, 1.0);
-    q.y = in ? __ldcs(reinterpret_cast<const double2*>(yp)) : zero;
+    const V zero = rows2_fill<V>(0.0f), one = rows2_fill<V>(1.0f);
+    q.y = in ? __ldcs(reinterpret_cast<const V*>(yp)) : zero;
     yp += S;
     if constexpr (AUX) {
-      q.w = in ? (wp ? __ldcs(reinterpret_cast<const double2*>(wp)) : one) : zero;
-      q.m = in ? (mp ? __ldcs(reinterpret_cast<const double2*>(mp)) : one) : zero;
+      q.w = in ? (wp ? __ldcs(reinterpret_cast<const V*>(wp)) : one) : zero;
+      q.m = in ? (mp ? __ldcs(reinterpret_cast<const V*>(mp)) : one) : zero;
       if (wp) wp += S;
       if (mp) mp += S;
     } else {
@@ -433,36 +451,42 @@ gram_dmma_side_kernel(const double* __restrict__ X, int64_t ldx, const double* _
     }
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-      q.z[b] = (in && live[b]) ? __ldcs(reinterpret_cast<const double2*>(colp[b])) : zero;
+      q.z[b] = (in && live[b]) ? __ldcs(reinterpret_cast<const V*>(colp[b])) : zero;
       colp[b] += S;
     }
     rl += S;
   };
   auto multiply = [&](const Batch& q) {
+    double2 z[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) z[b] = rows2_f64(q.z[b]);
+    const double2 yv = rows2_f64(q.y), mv = rows2_f64(q.m);
+    double2 wv = make_double2(1.0, 1.0);
+    if constexpr (AUX) wv = rows2_f64(q.w);
     double2 wy, wm;                                        // w y, w m (the weight enters every product once)
-    if constexpr (AUX) { wy = make_double2(q.w.x * q.y.x, q.w.y * q.y.y); wm = make_double2(q.w.x * q.m.x, q.w.y * q.m.y); }
-    else { wy = q.y; wm = q.m; }
-    yy = fma(wy.x, q.y.x, fma(wy.y, q.y.y, yy));
-    y1 = fma(wy.x, q.m.x, fma(wy.y, q.m.y, y1));
-    c11 = fma(wm.x, q.m.x, fma(wm.y, q.m.y, c11));
+    if constexpr (AUX) { wy = make_double2(wv.x * yv.x, wv.y * yv.y); wm = make_double2(wv.x * mv.x, wv.y * mv.y); }
+    else { wy = yv; wm = mv; }
+    yy = fma(wy.x, yv.x, fma(wy.y, yv.y, yy));
+    y1 = fma(wy.x, mv.x, fma(wy.y, mv.y, y1));
+    c11 = fma(wm.x, mv.x, fma(wm.y, mv.y, c11));
     // all block pairs for the even rows, then all for the odd rows: consecutive DMMAs never share an accumulator
     int idx = 0;
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
-      xy[i] = fma(q.z[i].x, wy.x, xy[i]);
-      x1[i] = fma(q.z[i].x, wm.x, x1[i]);
-      const double a0 = AUX ? q.z[i].x * q.w.x : q.z[i].x;
+      xy[i] = fma(z[i].x, wy.x, xy[i]);
+      x1[i] = fma(z[i].x, wm.x, x1[i]);
+      const double a0 = AUX ? z[i].x * wv.x : z[i].x;
 #pragma unroll
-      for (int j = i; j < NB; ++j) { dmma884(acc[idx][0], acc[idx][1], a0, q.z[j].x); ++idx; }
+      for (int j = i; j < NB; ++j) { dmma884(acc[idx][0], acc[idx][1], a0, z[j].x); ++idx; }
     }
     idx = 0;
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
-      xy[i] = fma(q.z[i].y, wy.y, xy[i]);
-      x1[i] = fma(q.z[i].y, wm.y, x1[i]);
-      const double a1 = AUX ? q.z[i].y * q.w.y : q.z[i].y;
+      xy[i] = fma(z[i].y, wy.y, xy[i]);
+      x1[i] = fma(z[i].y, wm.y, x1[i]);
+      const double a1 = AUX ? z[i].y * wv.y : z[i].y;
 #pragma unroll
-      for (int j = i; j < NB; ++j) { dmma884(acc[idx][0], acc[idx][1], a1, q.z[j].y); ++idx; }
+      for (int j = i; j < NB; ++j) { dmma884(acc[idx][0], acc[idx][1], a1, z[j].y); ++idx; }
     }
   };
 
@@ -553,43 +577,43 @@ constexpr int wide_depth(int nb, bool aux) {
   return aux ? auxd[nb - 1] : plain[nb - 1];
 }
 
-using SideFn = void (*)(const double*, int64_t, const double*, const double*, const double*, int64_t, int, double*);
-using WideFn = void (*)(const double*, int64_t, const double*, int64_t, const double*, const double*, int64_t, int, int, double*);
+template <typename T> using SideFn = void (*)(const T*, int64_t, const T*, const T*, const T*, int64_t, int, double*);
+template <typename T> using WideFn = void (*)(const T*, int64_t, const T*, int64_t, const T*, const T*, int64_t, int, int, double*);
 
 #ifdef PDSB_K2A_SWEEP   // sweep build (profiles/_ab): every depth 2..9 is instantiated, PDSB_K2A_DEPTH picks one per call
 static int k2a_sweep_depth() { const char* e = getenv("PDSB_K2A_DEPTH"); return e ? atoi(e) : 0; }
 #define PDSB_DEPTH_CASES(KERNEL, NBV, AUXV)                                                                          \
   switch (k2a_sweep_depth()) {                                                                                       \
-    case 2: return KERNEL<NBV, 2, 2, AUXV>; case 3: return KERNEL<NBV, 3, 2, AUXV>; case 4: return KERNEL<NBV, 4, 2, AUXV>; \
-    case 5: return KERNEL<NBV, 5, 2, AUXV>; case 6: return KERNEL<NBV, 6, 2, AUXV>; case 7: return KERNEL<NBV, 7, 2, AUXV>; \
-    case 8: return KERNEL<NBV, 8, 2, AUXV>; case 9: return KERNEL<NBV, 9, 2, AUXV>; default: break;                  \
+    case 2: return KERNEL<T, NBV, 2, 2, AUXV>; case 3: return KERNEL<T, NBV, 3, 2, AUXV>; case 4: return KERNEL<T, NBV, 4, 2, AUXV>; \
+    case 5: return KERNEL<T, NBV, 5, 2, AUXV>; case 6: return KERNEL<T, NBV, 6, 2, AUXV>; case 7: return KERNEL<T, NBV, 7, 2, AUXV>; \
+    case 8: return KERNEL<T, NBV, 8, 2, AUXV>; case 9: return KERNEL<T, NBV, 9, 2, AUXV>; default: break;                  \
   }
 #else
 #define PDSB_DEPTH_CASES(KERNEL, NBV, AUXV)
 #endif
 
-template <int NB, bool AUX> static SideFn side_fn() {
+template <typename T, int NB, bool AUX> static SideFn<T> side_fn() {
   PDSB_DEPTH_CASES(gram_dmma_side_kernel, NB, AUX)
-  return gram_dmma_side_kernel<NB, side_depth(NB, AUX), 2, AUX>;
+  return gram_dmma_side_kernel<T, NB, side_depth(NB, AUX), 2, AUX>;
 }
-template <int NB, bool AUX> static WideFn wide_fn() {
+template <typename T, int NB, bool AUX> static WideFn<T> wide_fn() {
   PDSB_DEPTH_CASES(gram_dmma_wide_kernel, NB, AUX)
-  return gram_dmma_wide_kernel<NB, wide_depth(NB, AUX), 2, AUX>;
+  return gram_dmma_wide_kernel<T, NB, wide_depth(NB, AUX), 2, AUX>;
 }
-static SideFn side_fn_rt(int nb, bool aux) {
+template <typename T> static SideFn<T> side_fn_rt(int nb, bool aux) {
   switch (nb) {
-    case 1: return aux ? side_fn<1, true>() : side_fn<1, false>(); case 2: return aux ? side_fn<2, true>() : side_fn<2, false>();
-    case 3: return aux ? side_fn<3, true>() : side_fn<3, false>(); case 4: return aux ? side_fn<4, true>() : side_fn<4, false>();
-    case 5: return aux ? side_fn<5, true>() : side_fn<5, false>(); case 6: return aux ? side_fn<6, true>() : side_fn<6, false>();
-    case 7: return aux ? side_fn<7, true>() : side_fn<7, false>(); default: return aux ? side_fn<8, true>() : side_fn<8, false>();
+    case 1: return aux ? side_fn<T, 1, true>() : side_fn<T, 1, false>(); case 2: return aux ? side_fn<T, 2, true>() : side_fn<T, 2, false>();
+    case 3: return aux ? side_fn<T, 3, true>() : side_fn<T, 3, false>(); case 4: return aux ? side_fn<T, 4, true>() : side_fn<T, 4, false>();
+    case 5: return aux ? side_fn<T, 5, true>() : side_fn<T, 5, false>(); case 6: return aux ? side_fn<T, 6, true>() : side_fn<T, 6, false>();
+    case 7: return aux ? side_fn<T, 7, true>() : side_fn<T, 7, false>(); default: return aux ? side_fn<T, 8, true>() : side_fn<T, 8, false>();
   }
 }
-static WideFn wide_fn_rt(int nb, bool aux) {
+template <typename T> static WideFn<T> wide_fn_rt(int nb, bool aux) {
   switch (nb) {
-    case 1: return aux ? wide_fn<1, true>() : wide_fn<1, false>(); case 2: return aux ? wide_fn<2, true>() : wide_fn<2, false>();
-    case 3: return aux ? wide_fn<3, true>() : wide_fn<3, false>(); case 4: return aux ? wide_fn<4, true>() : wide_fn<4, false>();
-    case 5: return aux ? wide_fn<5, true>() : wide_fn<5, false>(); case 6: return aux ? wide_fn<6, true>() : wide_fn<6, false>();
-    case 7: return aux ? wide_fn<7, true>() : wide_fn<7, false>(); default: return aux ? wide_fn<8, true>() : wide_fn<8, false>();
+    case 1: return aux ? wide_fn<T, 1, true>() : wide_fn<T, 1, false>(); case 2: return aux ? wide_fn<T, 2, true>() : wide_fn<T, 2, false>();
+    case 3: return aux ? wide_fn<T, 3, true>() : wide_fn<T, 3, false>(); case 4: return aux ? wide_fn<T, 4, true>() : wide_fn<T, 4, false>();
+    case 5: return aux ? wide_fn<T, 5, true>() : wide_fn<T, 5, false>(); case 6: return aux ? wide_fn<T, 6, true>() : wide_fn<T, 6, false>();
+    case 7: return aux ? wide_fn<T, 7, true>() : wide_fn<T, 7, false>(); default: return aux ? wide_fn<T, 8, true>() : wide_fn<T, 8, false>();
   }
 }
 #undef PDSB_DEPTH_CASES
@@ -607,20 +631,21 @@ static int launch_dmma(const double* X, int64_t ldx, const double* Y, int64_t ld
 }
 
 // The last n % 8 rows of the wide / side kernels: one CTA, one thread per entry of the partial.
+template <typename T>
 __global__ void __launch_bounds__(128)
-gram_rows_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
-                 const double* __restrict__ w, const double* __restrict__ mask, int rows, int p, int t,
+gram_rows_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ Y, int64_t ldy,
+                 const T* __restrict__ w, const T* __restrict__ mask, int rows, int p, int t,
                  double* __restrict__ out /* [q1*q1] */) {
   const int q1 = p + t + 1;
   auto at = [&](int c, int r) -> double {
-    if (c < p) return X[(int64_t)c * ldx + r];
-    if (c < p + t) return Y[(int64_t)(c - p) * ldy + r];
-    return mask ? mask[r] : 1.0;
+    if (c < p) return (double)X[(int64_t)c * ldx + r];
+    if (c < p + t) return (double)Y[(int64_t)(c - p) * ldy + r];
+    return mask ? (double)mask[r] : 1.0;
   };
   for (int e = threadIdx.x; e < q1 * q1; e += blockDim.x) {
     const int a = e / q1, b = e % q1;
     double v = 0.0;
-    for (int r = 0; r < rows; ++r) v = fma(w ? w[r] : 1.0, at(a, r) * at(b, r), v);   // a*b first: M stays symmetric bit for bit
+    for (int r = 0; r < rows; ++r) v = fma(w ? (double)w[r] : 1.0, at(a, r) * at(b, r), v);   // a*b first: M stays symmetric bit for bit
     out[e] = v;
   }
 }
@@ -642,30 +667,33 @@ gram_rows_kernel(const double* __restrict__ X, int64_t ldx, const double* __rest
 // cp.async ring in shared memory (38 %).  ncu (profiles/r02/k2a_*_ncu_metrics.csv, before the depth sweep): DMMA pipe 54-63 %
 // busy, DRAM 42-45 %, warps wait on the long scoreboard.
 // PDSB_K2A_KERNEL=8 forces the direct kernel, =1 the wide one also for a single target.
-static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64_t ldy, const double* w,
-                            const double* mask, int64_t n, int p, int t, double* M, cudaStream_t s) {
+template <typename T>
+static int moments_dmma(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, const T* mask, int64_t n, int p,
+                        int t, double* M, cudaStream_t s) {
+  constexpr bool F64 = sizeof(T) == 8;
   static const bool enabled = [] { const char* e = getenv("PDSB_K2A_DMMA"); return !(e && e[0] == '0'); }();
   static const int kern = [] { const char* e = getenv("PDSB_K2A_KERNEL"); return e ? atoi(e) : 2; }();
   const int q1 = p + t + 1;
   const int nb = (q1 + 7) / 8, nbx = (p + 7) / 8;
   if (!enabled || n < 1) return -1;
-  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  const bool aligned = kern != 8 && n >= 8 && al16(X) && al16(Y) && (ldx % 2 == 0) && (ldy % 2 == 0) && (!w || al16(w)) &&
-                       (!mask || al16(mask));
+  auto al2 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & (2 * sizeof(T) - 1)) == 0; };   // two rows per load
+  const bool aligned = kern != 8 && n >= 8 && al2(X) && al2(Y) && (ldx % 2 == 0) && (ldy % 2 == 0) && (!w || al2(w)) &&
+                       (!mask || al2(mask));
   const bool side = aligned && kern != 1 && t == 1 && nbx >= 1 && nbx <= 8 && nbx < nb;   // only when it saves a block
   const bool wide = aligned && !side && nb <= 8;
   if (!side && nb > 8) return -1;
+  if (!F64 && !side && !wide) return -1;                 // f32 columns that are not 8-byte aligned: the SIMT kernel
   const int64_t n_main = (side || wide) ? n - n % 8 : 0;
   const int64_t n_tail = n - n_main;
   // resident CTAs of the chosen instantiation (128 threads): from the registers ptxas used for it
-  SideFn sfn = nullptr; WideFn wfn = nullptr;
+  SideFn<T> sfn = nullptr; WideFn<T> wfn = nullptr;
   int per_sm = 4;
   const size_t ring_smem = ring_kernel_smem(side ? nbx : nb);
   if (side) {
-    sfn = side_fn_rt(nbx, w || mask);
+    sfn = side_fn_rt<T>(nbx, w || mask);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sfn, 128, ring_smem) != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 2; }
   } else if (wide) {
-    wfn = wide_fn_rt(nb, w != nullptr);
+    wfn = wide_fn_rt<T>(nb, w != nullptr);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wfn, 128, ring_smem) != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 2; }
   }
   const int grid_main = n_main ? (int)std::min<int64_t>(ceil_div(n_main, 32), (int64_t)sm_count() * per_sm) : 0;
@@ -687,15 +715,15 @@ static int moments_dmma_f64(const double* X, int64_t ldx, const double* Y, int64
   }
   if (rc) { dev_free(partials, s); return rc; }
   if (grid_tail > 0) {
-    const double* Xt = X + n_main; const double* Yt = Y + n_main;
-    const double* wt = w ? w + n_main : nullptr; const double* mt = mask ? mask + n_main : nullptr;
+    const T* Xt = X + n_main; const T* Yt = Y + n_main;
+    const T* wt = w ? w + n_main : nullptr; const T* mt = mask ? mask + n_main : nullptr;
     double* pt = partials + (size_t)grid_main * q1 * q1;
     if (n_main) {
-      gram_rows_kernel<<<1, 128, 0, s>>>(Xt, ldx, Yt, ldy, wt, mt, (int)n_tail, p, t, pt);
+      gram_rows_kernel<T><<<1, 128, 0, s>>>(Xt, ldx, Yt, ldy, wt, mt, (int)n_tail, p, t, pt);
       cudaError_t e = cudaGetLastError();
       count_launch();
       if (e != cudaSuccess) { set_error("gram_rows launch failed: %s", cudaGetErrorString(e)); rc = 1; }
-    } else {
+    } else if constexpr (F64) {
 #define PDSB_CALL(NBV) launch_dmma<NBV>(Xt, ldx, Yt, ldy, wt, mt, n_tail, p, t, grid_tail, pt, s)
       PDSB_NB_SWITCH(nb, PDSB_CALL)
 #undef PDSB_CALL
@@ -735,11 +763,9 @@ int moments_simt(const T* X, int64_t ldx, const T* Y, int64_t ldy, const T* w, c
                  int p, int t, double* M, cudaStream_t s, int64_t bstride) {
   const int q1 = p + t + 1;
   if (p < 0 || t < 0 || q1 > 260) { set_error("moments: p+t+1=%d out of range (max 260)", q1); return 1; }
-  if constexpr (sizeof(T) == 8) {
-    if (bstride == 0) {      // column-major f64: FP64 tensor-core path for up to 64 columns
-      const int rc = moments_dmma_f64(X, ldx, Y, ldy, w, mask, n, p, t, M, s);
-      if (rc >= 0) return rc;
-    }
+  if (bstride == 0) {        // column-major: FP64 tensor-core path for up to 64 columns (f32 columns are widened on the fly)
+    const int rc = moments_dmma<T>(X, ldx, Y, ldy, w, mask, n, p, t, M, s);
+    if (rc >= 0) return rc;
   }
   const int nt = (q1 + 3) / 4, ntp = nt * (nt + 1) / 2;
   const int maxt = (ntp + 255) / 256;

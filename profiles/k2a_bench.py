@@ -24,7 +24,7 @@ import os
 SHAPES = [(torch.float64, 20_000_000, 32), (torch.float32, 40_000_000, 32), (torch.float64, 50_000_000, 8),
           (torch.float64, 100_000, 4)]
 if os.environ.get("K2A_F64_ONLY"):
-    SHAPES = [(torch.float64, 20_000_000, 32), (torch.float64, 20_000_000, 30), (torch.float64, 50_000_000, 8), (torch.float64, 30_000_000, 16),
+    SHAPES = [(torch.float64, 20_000_000, 32), (torch.float32, 40_000_000, 32), (torch.float64, 20_000_000, 30), (torch.float64, 50_000_000, 8), (torch.float64, 30_000_000, 16),
               (torch.float64, 10_000_000, 62), (torch.float64, 10_000_000, 64), (torch.float64, 100_000, 4)]
 for dtype, n, p in SHAPES:
     Z = torch.randn((p + 1, n), device="cuda", dtype=dtype)

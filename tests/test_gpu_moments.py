@@ -174,3 +174,34 @@ def test_f64_moments_unaligned_columns_take_the_direct_kernel():
     M = dev.moments(Xo, Yo, n=n).cpu().numpy()
     scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
     assert np.max(np.abs(M - ref) / scale) < 1e-12
+
+
+@pytest.mark.parametrize("n,p,t,weighted,masked", [(200_131, 32, 1, True, False), (70_003, 20, 2, True, True),
+                                                   (123_457, 9, 1, True, True), (33_333, 64, 1, True, False),
+                                                   (50_006, 33, 6, False, False), (15, 40, 1, True, False),
+                                                   (90_001, 16, 1, False, True)])
+def test_f32_columns_on_the_dmma_kernels(n, p, t, weighted, masked):
+    """f32 fits the tcgen05 kernel does not take (weights, more than 4 targets) or that are forced off it: the same
+    DMMA kernels widen the f32 columns on the fly, so products and sums are exact to f64 rounding."""
+    import torch
+
+    from polars_ds_extension_b200 import device as dev
+    from polars_ds_extension_b200._lib import lib
+
+    Z, X, Y, ld = _mk(torch, n, p, t, torch.float32, 11 + p)
+    w = (torch.rand(ld, device="cuda", dtype=torch.float32) + 0.5) if weighted else None
+    mask = None
+    if masked:
+        mask = (torch.rand(ld, device="cuda") > 0.2).float()
+        Z[:, :] *= mask[None, :]
+    ref = _ref(X, Y, n, w=w, mask=mask)
+    lib().pdsb_set_moments_path(1)
+    try:
+        M1 = dev.moments(X, Y, n=n, w=w, mask=mask).cpu().numpy()
+        M2 = dev.moments(X, Y, n=n, w=w, mask=mask).cpu().numpy()
+    finally:
+        lib().pdsb_set_moments_path(0)
+    assert np.array_equal(M1, M2)
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    assert np.max(np.abs(M1 - ref) / scale) < 1e-12
+    assert np.array_equal(M1, M1.T)
