@@ -4,12 +4,14 @@
 // (/root/reference/src/utils/mod.rs:81-84 "tight group-by loops"; tests/test_linear_exprs.py:918-953).
 // Each call packs the group, builds X'X / X'y with a sequential matmul (lr_solvers.rs:186-190) and runs the gated
 // QR solve (:329-382).  Here the whole frame stays in HBM in key order and one launch sequence does all groups:
-//   pass 1  group moments: one warp per (group, chunk of <= CHUNK rows); lanes stride rows (coalesced column reads),
-//           the (p+2)(p+3)/2 moments live in registers (f32 FMA chains of <= CHUNK/32 terms -> f64 warp reduce);
-//           chunk partials are combined in a fixed order -> bit-reproducible, balanced for ragged group sizes.
-//   pass 2  batched solve: one thread per group on an interleaved (component-major) workspace so that every
-//           access is coalesced across groups: ridge, rank gate (ln|det| - sum ln diag <= ln tol), pivoted
-//           Householder QR (or Cholesky for solver="choleskey"), back-substitution.
+//   pass 0  work list: a group of len rows becomes ceil(len / CHUNK) items of EQUAL size; item -> rows map (one thread per item);
+//   pass 1  group moments: one warp per item, taken from a global counter by the warps of a persistent grid; lanes stride
+//           rows (coalesced column reads), the (p+2)(p+3)/2 moments live in registers (f32 FMA chains of <= CHUNK/32
+//           terms -> f64 warp reduce); item partials are combined in a fixed order -> bit-reproducible whatever warp ran them;
+//   pass 2  batched solve: one thread per group on an interleaved (component-major) workspace — shared memory of a
+//           32-thread CTA up to ~20 coefficients, global memory (coalesced across groups) above: ridge, rank gate
+//           (ln|det| - sum ln diag <= ln tol), pivoted Householder QR (or Cholesky for solver="choleskey"),
+//           back-substitution, coordinate descent / NNLS per group.
 // HBM-bound: algorithmic bytes per row = (p+1) * s.
 #include "../common.h"
 #include "kernels.h"
@@ -173,81 +175,6 @@ __global__ void __launch_bounds__(128) small_reduce_kernel(const double* __restr
     const int j = i + rem;
     M[(size_t)i * q1 + j] = red[0];
     M[(size_t)j * q1 + i] = red[0];
-  }
-}
-
-// 16-byte-load variant (PDSB_K5_VEC=1; measured slower than the scalar kernel, kept as the recorded experiment): a lane owns V = 16 / sizeof(T)
-// CONSECUTIVE rows per load, so one warp instruction reads 512 contiguous bytes of a column and a trip of U loads per
-// column reads U x 512 B of it.  The scalar kernel above touches every column in 128-byte pieces; with p + 1 column
-// streams per warp and thousands of warps that pattern capped at ~4.3 TB/s (65 % of the HBM peak, the same ceiling the
-// Gram kernel measured on column-major frames) — longer runs per column are what DRAM pages want.
-// Rows of the 16-byte groups that fall outside [r0, r1) are masked (groups start at arbitrary rows).
-template <typename T> struct Vec16;
-template <> struct Vec16<float> { using type = float4; static constexpr int V = 4; };
-template <> struct Vec16<double> { using type = double2; static constexpr int V = 2; };
-__device__ __forceinline__ float vget(const float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
-__device__ __forceinline__ double vget(const double2& v, int e) { return e == 0 ? v.x : v.y; }
-
-template <typename T, int P>
-__global__ void __launch_bounds__(256)
-group_moments_vec_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y,
-                         const int64_t* __restrict__ offsets, const int64_t* __restrict__ item_start,
-                         int64_t n_groups, int64_t n_items, int64_t n, double* __restrict__ part /* [NM][n_items] */) {
-  using VT = typename Vec16<T>::type;
-  constexpr int V = Vec16<T>::V;
-  constexpr int Q1 = P + 2;
-  constexpr int NM = Q1 * (Q1 + 1) / 2;
-  constexpr int U = 2;                                   // loads per column and trip
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t last_vec = ((n - 1) / V) * V;            // last 16-byte group that starts inside the columns
-  for (int64_t item = warp_global; item < n_items; item += nwarps) {
-    int64_t lo = 0, hi = n_groups;
-    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (item_start[mid] <= item) lo = mid; else hi = mid; }
-    const int64_t g = lo;
-    int64_t r0, r1;
-    item_range(offsets, item_start, g, item, r0, r1);
-    T acc[NM];
-#pragma unroll
-    for (int k = 0; k < NM; ++k) acc[k] = T(0);
-    for (int64_t b = (r0 / V) * V + (int64_t)V * lane; b < r1; b += (int64_t)32 * V * U) {
-      VT z[U][P + 1];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t bb = min(b + (int64_t)32 * V * u, last_vec);      // clamped address; rows past r1 are masked below
-#pragma unroll
-        for (int c = 0; c < P; ++c) z[u][c] = *reinterpret_cast<const VT*>(X + (int64_t)c * ldx + bb);
-        z[u][P] = *reinterpret_cast<const VT*>(y + bb);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const int64_t rr = b + (int64_t)32 * V * u + e;
-          T row[Q1];
-          T probe = T(0);
-#pragma unroll
-          for (int c = 0; c <= P; ++c) { row[c] = vget(z[u][c], e); probe = fma(row[c], T(0), probe); }
-          // null rows arrive as NaN (null_policy="skip"): they drop out of their group -> the whole row becomes 0
-          const bool use = (rr >= r0) && (rr < r1) && (probe == T(0));
-#pragma unroll
-          for (int c = 0; c <= P; ++c) row[c] = use ? row[c] : T(0);
-          row[P + 1] = use ? T(1) : T(0);
-          int k = 0;
-#pragma unroll
-          for (int i = 0; i < Q1; ++i)
-#pragma unroll
-            for (int j = i; j < Q1; ++j) { acc[k] = fma(row[i], row[j], acc[k]); ++k; }
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < NM; ++k) {
-      double v = (double)acc[k];
-      for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      if (lane == 0) part[(size_t)k * n_items + item] = v;
-    }
   }
 }
 
@@ -729,11 +656,8 @@ int launch_moments_p(const T* X, int64_t ldx, const T* y, const int64_t* offsets
   int grid = (int)std::min<int64_t>(ceil_div(warps, 8), (int64_t)sm_count() * 16);
   if (grid < 1) grid = 1;
   constexpr int V = 16 / (int)sizeof(T);
-  // measured (B200, C3: 1e8 rows x 8 f32, ~1e4 groups): scalar kernel 0.995 ms, 16-byte-load kernel 1.33 ms (140 registers,
-  // two 16-byte loads per column in flight instead of four 4-byte ones) -> the scalar kernel stays the default
-  static const bool vec_on = [] { const char* e = getenv("PDSB_K5_VEC"); return e && e[0] == '1'; }();
-  const bool aligned = (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0) &&
-                       (ldx % V == 0) && (ldx >= ((n + V - 1) / V) * V);
+  // (a 16-byte-load variant of the register kernel measured 1.33 ms against 0.995 ms on C3 in round 2 — 140 registers, two
+  // 16-byte loads per column in flight instead of four 4-byte ones — and was removed)
   // measured (B200, C3): register kernel 0.996 ms (56 % of HBM); staged kernel 1.38 ms scalar rows -> 1.20 ms packed row
   // pairs -> 1.09 ms with the f32 per-item tree sum (51 %): 110 accumulator registers leave one CTA per SM, and the
   // per-item CTA-wide reduction drains the ring every 16 tiles.  The register kernel stays the default; PDSB_K5_STAGED=1
@@ -760,10 +684,7 @@ int launch_moments_p(const T* X, int64_t ldx, const T* y, const int64_t* offsets
       launched = true;
     }
   }
-  if (launched) {
-  } else if (vec_on && aligned && P <= 10)
-    group_moments_vec_kernel<T, P><<<grid, 256, 0, s>>>(X, ldx, y, offsets, item_start, n_groups, n_items, n, part);
-  else {
+  if (!launched) {
     // PDSB_K5_MODE: 0 = binary search + fixed stride (round 1), 1 = precomputed rows, 2 = work queue, 3 = both (default;
     // C3 in one call: 0.861 / 0.852 / 0.810 / 0.805 ms, profiles/r02/k5_mode_sweep.txt)
     static const int mode = [] { const char* e = getenv("PDSB_K5_MODE"); return e ? atoi(e) : 3; }();
