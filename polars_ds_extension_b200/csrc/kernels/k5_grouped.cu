@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(128)
 group_moments_generic_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y,
                              const int64_t* __restrict__ offsets, const int64_t* __restrict__ item_start,
                              int64_t n_groups, int64_t n_items, int p, double* __restrict__ part) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int q1 = p + 2;
   const int nm = q1 * (q1 + 1) / 2;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
