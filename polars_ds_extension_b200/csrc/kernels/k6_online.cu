@@ -169,6 +169,7 @@ chain_sums_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y,
   // per-lane sums are 32-term f32 FMA chains — the same precision pass C's scan works in, and a window only ever sees the
   // DIFFERENCE of a few chain sums, so the error does not grow with n.  (With f64 products this pass ran at 1.36 ms per
   // 1e8 x 9 f32 = 40 % of the HBM peak: 45 DFMA + 9 conversions per row on a part whose FP64 pipe is narrow.)
+  constexpr int NMP = (NM + 31) / 32 * 32;               // padded to whole 32s for the transpose-reduce at the end
   T v[NM];
 #pragma unroll
   for (int c = 0; c < NM; ++c) v[c] = T(0);
@@ -207,13 +208,28 @@ chain_sums_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ y,
       v[q] += fin ? T(1) : T(0);
     }
   }
+  // Transpose-reduce over the warp, in f64: at every step a lane hands the half of its values it does not keep to its
+  // partner and adds the partner's half it keeps -> NMP - NMP / 32 double shuffles and DADDs for all NM sums, where the
+  // butterfly per value cost 5 of each (a quarter of this kernel's instructions at NM = 46).  (The same tree in f32 was
+  // 2 % faster still but put one rolling parity case outside the two-sided f32 rule of tests/parity_rule.py.)
+  double dv[NMP];
 #pragma unroll
-  for (int c = 0; c < NM; ++c) {
-    double x = (double)v[c];
+  for (int c = 0; c < NMP; ++c) dv[c] = c < NM ? (double)v[c] : 0.0;
 #pragma unroll
-    for (int off = 16; off; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-    if (lane == (c & 31)) S[(size_t)c * nchains + k] = x;
+  for (int s = 16, m = NMP / 2; s >= 1; s >>= 1, m >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+      const double give = upper ? dv[i] : dv[i + m];
+      const double keep = upper ? dv[i + m] : dv[i];
+      dv[i] = keep + __shfl_xor_sync(0xffffffffu, give, s);
+    }
   }
+  const int cbase = ((lane >> 4) & 1) * (NMP / 2) + ((lane >> 3) & 1) * (NMP / 4) + ((lane >> 2) & 1) * (NMP / 8) +
+                    ((lane >> 1) & 1) * (NMP / 16) + (lane & 1) * (NMP / 32);
+#pragma unroll
+  for (int j = 0; j < NMP / 32; ++j)
+    if (cbase + j < NM) S[(size_t)(cbase + j) * nchains + k] = dv[j];
 }
 
 // ---------------- pass B: exclusive scan along tiles, one block per component ----------------
