@@ -193,11 +193,27 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ helpers
-def host_threads() -> int:
+def cpu_quota() -> float:
+    """CPUs of the cgroup quota (cpu.max "quota period"), 0.0 when there is none."""
     try:
-        return len(os.sched_getaffinity(0))
+        a, b = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return 0.0 if a == "max" else float(a) / float(b)
     except Exception:
-        return os.cpu_count() or 1
+        return 0.0
+
+
+def host_threads() -> int:
+    """Threads the CPU arm runs on: the cores this process may use — affinity mask, cut to the cgroup CPU quota when there
+    is one (the B200 boxes report 128 cores under a 16-CPU quota; threads beyond the quota only get throttled).
+    PDSB_BENCH_THREADS overrides."""
+    if os.environ.get("PDSB_BENCH_THREADS"):
+        return max(1, int(os.environ["PDSB_BENCH_THREADS"]))
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    q = cpu_quota()
+    return max(1, min(n, int(q + 0.5))) if q >= 1.0 else n
 
 
 def hbm_peak():

@@ -9,6 +9,7 @@
 // cudaHostRegister) skip all of this.
 #include "../common.h"
 #include "host.h"
+#include <cstdio>
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
@@ -21,7 +22,7 @@ namespace {
 
 constexpr size_t PIECE = size_t(8) << 20;
 constexpr size_t STAGE_MIN = size_t(1) << 20;      // smaller pageable ranges: the driver's path is fine
-constexpr int MAX_W = 16;
+constexpr int MAX_W = 32;
 
 struct StageRes {
   void* slot[2] = {nullptr, nullptr};
@@ -60,14 +61,41 @@ int ensure_res(StagePool* P, int w) {
   return 0;
 }
 
+// CPUs this process may actually burn: the cgroup CPU quota (containers: cpu.max "quota period"), else 0 = no limit.
+// hardware_concurrency() reports the host's cores (128 on the B200 boxes) also when the quota is 16, and staging threads
+// beyond the quota are throttled as a group: measured on such a box (profiles/r02/h2d_threads_*.txt, 13.2 GB pageable,
+// pinned rate 273 ms): 4 threads 358 ms, 6: 291, 8: 315, 10: 297, 12: 325, 16: 374, 24: 368, 32: 688.
+double cgroup_cpu_quota() {
+  double q = 0.0;
+  if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {            // cgroup v2
+    char a[64] = {0};
+    double period = 0.0;
+    if (fscanf(f, "%63s %lf", a, &period) == 2 && strcmp(a, "max") != 0 && period > 0.0) q = atof(a) / period;
+    fclose(f);
+    return q;
+  }
+  FILE* fq = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r");    // cgroup v1
+  FILE* fp = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r");
+  if (fq && fp) {
+    double quota = -1.0, period = 0.0;
+    if (fscanf(fq, "%lf", &quota) == 1 && fscanf(fp, "%lf", &period) == 1 && quota > 0.0 && period > 0.0) q = quota / period;
+  }
+  if (fq) fclose(fq);
+  if (fp) fclose(fp);
+  return q;
+}
+
 int staging_threads() {
   static int w = [] {
     const char* e = getenv("PDS_B200_H2D_THREADS");
     if (e && atoi(e) > 0) return std::min(MAX_W, atoi(e));
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     DeviceGroup* g = active_group();
-    const unsigned share = hw / (2 * (g ? (unsigned)g->devices.size() : 1u));
-    return (int)std::min<unsigned>(MAX_W, std::max<unsigned>(2, share));
+    const unsigned ndev = g ? (unsigned)g->devices.size() : 1u;
+    const double quota = cgroup_cpu_quota();
+    if (quota >= 1.0)      // ~0.4 of the quota: the copies need headroom for the DMA completion work and the caller
+      return (int)std::min<unsigned>(MAX_W, std::max<unsigned>(2, (unsigned)(quota * 0.4 / ndev + 0.5)));
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    return (int)std::min<unsigned>(16, std::max<unsigned>(2, hw / (2 * ndev)));
   }();
   return w;
 }
