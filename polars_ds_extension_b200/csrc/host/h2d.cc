@@ -90,7 +90,9 @@ int staging_threads() {
     const char* e = getenv("PDS_B200_H2D_THREADS");
     if (e && atoi(e) > 0) return std::min(MAX_W, atoi(e));
     DeviceGroup* g = active_group();
-    const unsigned ndev = g ? (unsigned)g->devices.size() : 1u;
+    unsigned ndev = g ? (unsigned)g->devices.size() : 1u;
+    // one process per GPU (torchrun): the node's CPUs are shared by LOCAL_WORLD_SIZE such processes
+    if (const char* lws = getenv("LOCAL_WORLD_SIZE")) ndev = std::max<unsigned>(ndev, (unsigned)std::max(1, atoi(lws)));
     const double quota = cgroup_cpu_quota();
     if (quota >= 1.0)      // ~0.4 of the quota: the copies need headroom for the DMA completion work and the caller
       return (int)std::min<unsigned>(MAX_W, std::max<unsigned>(2, (unsigned)(quota * 0.4 / ndev + 0.5)));
