@@ -48,6 +48,23 @@ for f64 in (False, True):
     gid = np.repeat(np.arange(10), 500)
     gpu.group_eval(df.with_columns(g=gid), "g", pds.lin_reg(*xs, target="y", add_bias=True), fast=True)
     gpu.group_eval(df.with_columns(g=gid), "g", pds.lin_reg(*xs, target="y", l1_reg=0.01), fast=True)
+# device layer: the DMMA ring kernels (side / wide, every block-count class, weights / mask, n % 8 != 0), f64 and f32 columns
+for tdt in (torch.float64, torch.float32):
+    for p_, t_, wt, mk in [(8, 1, False, False), (32, 1, True, True), (30, 2, True, False), (64, 1, False, True), (62, 1, False, False),
+                           (16, 1, True, False), (46, 1, False, False)]:
+        n_, ld_ = 4099, 4128
+        Zd = torch.randn((p_ + t_, ld_), device="cuda", dtype=tdt)
+        w_ = (torch.rand(ld_, device="cuda", dtype=tdt) + 0.5) if wt else None
+        m_ = (torch.rand(ld_, device="cuda") > 0.2).to(tdt) if mk else None
+        if tdt == torch.float32:
+            lib().pdsb_set_moments_path(1)
+        dev.moments(Zd[:p_], Zd[p_:], n=n_, w=w_, mask=m_)
+        lib().pdsb_set_moments_path(0)
+# grouped path with several items per group (work queue, precomputed item rows, shared-memory solve)
+cfg.LIN_REG_EXPR_F64 = False
+dfg, xsg = frame(27000, 8, np.float32)
+gidg = np.repeat(np.arange(3), 9000)
+gpu.group_eval(dfg.with_columns(g=gidg), "g", pds.lin_reg(*xsg, target="y", add_bias=True), fast=True)
 # device layer: frames
 Z = torch.randn((33, 8192), device="cuda")
 fr = dev.to_frame(Z, n=8192)
