@@ -1,11 +1,19 @@
-// K2a — generic SIMT moments kernel:  M = [X|Y|1]^T diag(w) [X|Y|1]   (q1 x q1, f64, row-major)
+// K2a — moments of column-major data:  M = [X|Y|1]^T diag(w) [X|Y|1]   (q1 x q1, f64, row-major)
 //
 // Replaces the reference's get_xtx_with_lambda + build_xty + column sums
 // (/root/reference/src/linear/lr/lr_solvers.rs:183-211, 262-278, 483-484) and x^T w x
 // (src/num_ext/linear_regression.rs:1026-1027) with ONE pass over the data.
 //
-// This is the path for f64 data, weighted fits, tiny inputs and shapes the tcgen05 kernel does not take
-// (k2_gram_tcgen05.cu is the f32 headline path).  Layout: X col-major [n x p] (ldx), Y col-major [n x t] (ldy).
+// This file is the path for f64 data (the reference's default dtype), weighted fits, more than 4 targets, tiny inputs and
+// every shape the tcgen05 kernel does not take (k2_gram_tcgen05.cu is the f32 headline path).  Three kernel families,
+// chosen in moments_simt / moments_dmma below:
+//   * gram_dmma_side_kernel / gram_dmma_wide_kernel — FP64 tensor cores (mma.sync.m8n8k4, SASS DMMA), up to 64 columns,
+//     f64 and (widened on the fly) f32 columns, 16-byte loads through a register ring: the production kernels
+//     (f64 with 32 features: 73 % of the HBM peak; 8 features: 93 %);
+//   * gram_dmma_kernel — the same blocks with scalar loads, for columns that are not aligned for two-row loads;
+//   * gram_simt_kernel — DFMA / FFMA register tiles, any width up to 260 columns and row-blocked frames (bstride != 0).
+//
+// gram_simt_kernel: X col-major [n x p] (ldx), Y col-major [n x t] (ldy).
 // Each CTA walks row tiles of TILE_R rows: tile -> shared memory (row-major, row stride S), every thread owns
 // up to MAXT 4x4 blocks of the upper triangle; per tile the block is accumulated in T (a short FMA chain)
 // and then added to f64 accumulators, so f32 rounding never grows with n.  When there are fewer blocks than threads
