@@ -36,3 +36,28 @@ def test_ref_port_gate():
     cols = [x * 2, x, (x * 3).astype(np.float32)]          # collinear features -> the rank gate fires -> None
     c, _, _, _ = ref_port.lr_pred_f32(cols)
     assert c is None
+
+
+def test_cpu_arm_thread_count_follows_quota_and_override(monkeypatch, tmp_path):
+    """bench.py's CPU arm runs on the CPUs the process may use: the affinity mask cut to the cgroup quota (the B200 boxes
+    report 128 cores under `cpu.max 1600000 100000`), PDSB_BENCH_THREADS overrides."""
+    import builtins
+
+    import bench
+
+    monkeypatch.setenv("PDSB_BENCH_THREADS", "5")
+    assert bench.host_threads() == 5
+    monkeypatch.delenv("PDSB_BENCH_THREADS")
+    real_open = builtins.open
+    fake = tmp_path / "cpu.max"
+
+    def fake_open(path, *a, **k):
+        return real_open(fake if path == "/sys/fs/cgroup/cpu.max" else path, *a, **k)
+
+    monkeypatch.setattr(builtins, "open", fake_open)
+    fake.write_text("200000 100000\n")
+    assert bench.cpu_quota() == 2.0
+    assert bench.host_threads() <= 2
+    fake.write_text("max 100000\n")
+    assert bench.cpu_quota() == 0.0
+    assert bench.host_threads() >= 1
