@@ -60,7 +60,8 @@ int64_t pdsb_kernel_launch_count(void);
 /* plugin layer: results exported to the caller whose buffers have not been released yet (ownership tests) */
 int64_t pdsb_plugin_live_results(void);
 /* which kernel handled the last pdsb_dev_moments_f32 call on this thread: 1 = tcgen05/TMA Gram kernel, 3 = register-moments
- * kernel (<= 10 features, one target, >= 65536 rows, no mask / weights), 0 = generic SIMT kernel */
+ * kernel (<= 10 features, one target, >= 65536 rows, no mask / weights), 0 = the generic path of k2_gram_simt.cu (FP64
+ * tensor-core ring kernels for up to 64 aligned columns — f32 columns are widened on the fly —, SIMT register tiles otherwise) */
 int pdsb_last_moments_path(void);
 /* force a path for the f32 moments: 0 auto, 1 simt, 2 tcgen05 (tests / ncu) */
 void pdsb_set_moments_path(int path);
