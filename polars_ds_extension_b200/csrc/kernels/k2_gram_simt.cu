@@ -286,7 +286,7 @@ template <typename V> __device__ __forceinline__ V rows2_fill(float a) { V v; v.
 // k index can be any four rows, so the .x halves (rows r0 + {0, 2, 4, 6}) make one m8n8k4 step and the .y halves the
 // next.  DEPTH batches live in a register ring (the loop is unrolled over the ring, so every index is static): DEPTH - 1
 // batches = 8 (DEPTH - 1) rows per warp are in flight while one is multiplied.  The mask is just the "ones" column read
-// from memory.  128-thread CTAs, MINB per SM.  Needs 16-byte aligned columns and even leading dimensions.
+// from memory.  128-thread CTAs, as many per SM as the registers of the instantiation allow (occupancy query at launch).  Needs 16-byte aligned columns and even leading dimensions.
 // T = float: the same kernel for f32 columns (8-byte loads, converted when multiplied): weighted / many-target f32 fits
 // that the tcgen05 kernel does not take get exact f64 products and sums at the DMMA rate instead of the SIMT kernel's 15 %.
 template <typename T, int NB, int DEPTH, int MINB, bool WEIGHTED>
